@@ -1,0 +1,333 @@
+// K2/K3/K4: implicit-GEMM convolution for sm_100a.
+//
+//   D[M = pixels, N = Cout] = A[M, K] * W[Cout, K]^T        K ordered (r, s, cin)
+//
+// replaces, per conv, the reference's cuDNN conv + BatchNorm + ReLU (+ residual add) chain
+// (torchvision models/resnet.py:143-163 Bottleneck.forward, :268-271 stem; called from
+// src/preprocess_resnet_features.py:296 `backbone(x)`).  BN is folded into W and a per-channel fp32 bias
+// on the host, so the epilogue is  y = relu?(acc + bias [+ residual]).
+//
+// Structure: one persistent CTA per SM, 6 warps, warp-specialised.
+//   warp 0   TMA producer   A tile via tiled / im2col / stem-window tensor maps, W tile via a 2-D map, both
+//                           K-major with hardware swizzle, NSTAGE-deep mbarrier ring
+//   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM
+//                           accumulator; tcgen05.commit releases smem slots / publishes the accumulator
+//   warp 2-5 epilogue       tcgen05.ld -> bias/residual/ReLU -> bf16 -> global (or fused global-avg-pool)
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace phdfxk {
+
+enum ConvMode : int {
+  MODE_TILED = 0,   // 1x1 stride 1: A is the [M, Cin] activation matrix itself
+  MODE_IM2COL = 1,  // 3x3 (any stride) and strided 1x1: TMA im2col mode over NHWC
+  MODE_STEM = 2,    // 7x7/2 stem: per filter row an 8-pixel x 4-channel window, overlapping-stride 5-D map
+  MODE_GAP = 3,     // last 1x1 conv: tile = 2 whole frames (98 rows), epilogue emits the 7x7 mean in fp32
+};
+
+struct ConvParams {
+  int M;           // valid GEMM rows in this launch (pixels; frames*98/2... see mode)
+  int Cout;        // GEMM N
+  int num_kb;      // K blocks per tile
+  int kb_per_tap;  // Cin / 64 (im2col)
+  int S;           // filter width (im2col)
+  int P, Q;        // output spatial size
+  int stride, pad;
+  int m_tiles, n_tiles;
+  int relu;
+  int n_frames;
+  const float* bias;               // [Cout] folded BN bias
+  const __nv_bfloat16* residual;   // nullable, same layout as out
+  __nv_bfloat16* out;              // [M, Cout] NHWC activations
+  float* feats;                    // MODE_GAP: [n_frames, Cout]
+};
+
+constexpr int kBlockM = 128;
+constexpr int kNumThreads = 192;
+constexpr int kGapRowsPerFrame = 49;
+constexpr int kGapRows = 98;
+constexpr int kStemTileQ = 16, kStemTileP = 8, kStemOut = 112, kStemTilesPerFrame = (112 / 16) * (112 / 8);
+
+template <int BN, int MODE>
+struct ConvCfg {
+  static constexpr int ROWB = (MODE == MODE_STEM) ? 64 : 128;  // bytes per smem operand row (= BLOCK_K bf16)
+  static constexpr int BLOCK_K = ROWB / 2;
+  static constexpr int A_BYTES = kBlockM * ROWB;
+  static constexpr int B_BYTES = BN * ROWB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int A_TX = ((MODE == MODE_GAP) ? kGapRows : kBlockM) * ROWB;
+  static constexpr int SCRATCH_BYTES = (MODE == MODE_GAP) ? kBlockM * 33 * 4 : 0;
+  static constexpr int TAIL_BYTES = 2048 + 2 * BN * 4 + SCRATCH_BYTES;  // barriers + bias double buffer + scratch
+  static constexpr int SMEM_BUDGET = 200 * 1024;
+  static constexpr int NSTAGE_RAW = (SMEM_BUDGET - TAIL_BYTES - 1024) / STAGE_BYTES;
+  static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + TAIL_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;                // power of two for BN in {64,128,256}
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const ConvParams p) {
+  using Cfg = ConvCfg<BN, MODE>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  static_assert(NSTAGE >= 2, "pipeline needs at least two stages");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tail = smem + NSTAGE * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);  // [NSTAGE]
+  uint64_t* empty_bar = full_bar + NSTAGE;                 // [NSTAGE]
+  uint64_t* tmem_full = empty_bar + NSTAGE;                // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                    // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tail + 2048);   // [2][BN]
+  float* s_scratch = s_bias + 2 * BN;                      // MODE_GAP: [128][33]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.n_tiles;
+        const int n_blk = tile - m_blk * p.n_tiles;
+        // per-tile A coordinates
+        int cw = 0, ch = 0, cn = 0;
+        if (MODE == MODE_IM2COL) {
+          const int m0 = m_blk * kBlockM;
+          const int pq = p.P * p.Q;
+          cn = m0 / pq;
+          const int rem = m0 - cn * pq;
+          const int p0 = rem / p.Q;
+          const int q0 = rem - p0 * p.Q;
+          cw = q0 * p.stride - p.pad;
+          ch = p0 * p.stride - p.pad;
+        } else if (MODE == MODE_STEM) {
+          cn = m_blk / kStemTilesPerFrame;
+          const int t = m_blk - cn * kStemTilesPerFrame;
+          ch = (t / (kStemOut / kStemTileQ)) * kStemTileP;  // p0
+          cw = (t % (kStemOut / kStemTileQ)) * kStemTileQ;  // q0
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_TX + Cfg::B_BYTES);
+          if (MODE == MODE_TILED) {
+            tma_load_2d(&mapA, &full_bar[stage], sA, kb * Cfg::BLOCK_K, m_blk * kBlockM);
+            tma_load_2d(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
+          } else if (MODE == MODE_IM2COL) {
+            const int tap = kb / p.kb_per_tap;
+            const int cb = kb - tap * p.kb_per_tap;
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            tma_load_im2col_4d(&mapA, &full_bar[stage], sA, cb * Cfg::BLOCK_K, cw, ch, cn,
+                               static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+            tma_load_2d(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
+          } else if (MODE == MODE_STEM) {
+            const int d = kb - 3;  // input row = 2*p + d
+            tma_load_5d(&mapA, &full_bar[stage], sA, 0, cw, d & 1, ch + (d >> 1), cn);
+            tma_load_2d(&mapB, &full_bar[stage], sB, 0, kb * BN);
+          } else {  // MODE_GAP
+            tma_load_3d(&mapA, &full_bar[stage], sA, kb * Cfg::BLOCK_K, 0, m_blk * 2);
+            tma_load_2d(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
+          }
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
+            const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, Cfg::ROWB);
+            const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, Cfg::ROWB);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;     // row of the 128-row tile owned by this thread
+    const int et = threadIdx.x - 64;      // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.n_tiles;
+      const int n_blk = tile - m_blk * p.n_tiles;
+      const int n_base = n_blk * BN;
+      float* sb = s_bias + (it & 1) * BN;
+      for (int i = et; i < BN; i += 128) sb[i] = __ldg(&p.bias[n_base + i]);
+      named_barrier_sync(1, 128);
+
+      // output row addressing
+      bool row_ok;
+      size_t row_off;  // element offset of this thread's output row
+      if (MODE == MODE_STEM) {
+        const int n = m_blk / kStemTilesPerFrame;
+        const int t = m_blk - n * kStemTilesPerFrame;
+        const int pp = (t / (kStemOut / kStemTileQ)) * kStemTileP + (row >> 4);
+        const int qq = (t % (kStemOut / kStemTileQ)) * kStemTileQ + (row & 15);
+        row_ok = n < p.n_frames;
+        row_off = ((static_cast<size_t>(n) * kStemOut + pp) * kStemOut + qq) * p.Cout;
+      } else if (MODE == MODE_GAP) {
+        const int m = m_blk * kGapRows + row;
+        row_ok = (row < kGapRows) && (m < p.M);
+        row_off = static_cast<size_t>(m) * p.Cout;
+      } else {
+        const int m = m_blk * kBlockM + row;
+        row_ok = m < p.M;
+        row_off = static_cast<size_t>(m) * p.Cout;
+      }
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, v);
+        // residual (bf16) for these 32 channels, issued before waiting on the TMEM load
+        uint4 rv[4];
+        const bool has_res = (p.residual != nullptr) && row_ok;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n_base + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rv[j] = __ldg(rp + j);
+        }
+        tmem_ld_wait();
+        float f[32];
+        const float4* sb4 = reinterpret_cast<const float4*>(sb + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = sb4[j];
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              f[8 * j + 2 * q + 0] += bf16_lo(w[q]);
+              f[8 * j + 2 * q + 1] += bf16_hi(w[q]);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (MODE == MODE_GAP) {
+          // deterministic in-CTA mean over the 49 rows of each of the tile's two frames
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s_scratch[row * 33 + j] = row_ok ? f[j] : 0.0f;
+          named_barrier_sync(2, 128);
+          if (et < 64) {
+            const int fr = et >> 5;
+            const int col = et & 31;
+            const int frame = m_blk * 2 + fr;
+            float acc_sum = 0.0f;
+            for (int r = 0; r < kGapRowsPerFrame; ++r) acc_sum += s_scratch[(fr * kGapRowsPerFrame + r) * 33 + col];
+            if (frame < p.n_frames)
+              p.feats[static_cast<size_t>(frame) * p.Cout + n_base + c * 32 + col] =
+                  acc_sum * (1.0f / kGapRowsPerFrame);
+          }
+          named_barrier_sync(3, 128);
+        } else if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + row_off + n_base + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            op[j] = o;
+          }
+        }
+      }
+      // release the accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace phdfxk

@@ -1,0 +1,151 @@
+// K1 and the other HBM-bound kernels of the path: uint8 crop + bilinear resize + ImageNet normalise,
+// NCHW-fp32 -> stem-layout repack (Seam A), 3x3/2 max-pool.
+//
+// Stem input layout ("NHWC4p"): bf16 [N][224][232][4]; pixel column wp = w + 4 (4 zero pixels on each side so the
+// 7-tap window of the stem conv never leaves the row), channel 3 is zero padding.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace phdfxk {
+
+constexpr int kImg = 224;        // network input side
+constexpr int kStemWPad = 232;   // padded row length in pixels
+constexpr int kStemLeftPad = 4;
+
+// Mirrors src/dataset.py:141-152 (_crop_and_resize_video_uint8) + :242-245/:429 (Normalize):
+//   crop [top:top+h, left:left+w] -> F.resize(224, bilinear, antialias=False) evaluated in fp32 and ROUNDED
+//   half-to-even back to uint8 (torchvision transforms/_functional_tensor.py:462-472,536-540) -> /255 ->
+//   (x - mean) / std  (fp32) -> bf16.
+// ATen's bilinear (align_corners=False): src = max(0, scale*(dst+0.5)-0.5), scale = in/out in fp32;
+//   value = wh0*(ww0*v00 + ww1*v01) + wh1*(ww0*v10 + ww1*v11), each product/sum rounded to fp32 (no FMA).
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
+                                     const int32_t* __restrict__ boxes, int flip_w, __nv_bfloat16* __restrict__ out) {
+  const int total = n_frames * kImg * kStemWPad;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int wp = idx % kStemWPad;
+    const int y = (idx / kStemWPad) % kImg;
+    const int n = idx / (kStemWPad * kImg);
+    uint2 o = make_uint2(0u, 0u);
+    int x = wp - kStemLeftPad;
+    if (x >= 0 && x < kImg) {
+      if (flip_w) x = kImg - 1 - x;
+      int top = 0, left = 0, bh = H, bw = W;
+      if (boxes != nullptr) {
+        top = boxes[4 * n + 0];
+        left = boxes[4 * n + 1];
+        bh = boxes[4 * n + 2];
+        bw = boxes[4 * n + 3];
+      }
+      const float scale_h = __fdiv_rn(static_cast<float>(bh), static_cast<float>(kImg));
+      const float scale_w = __fdiv_rn(static_cast<float>(bw), static_cast<float>(kImg));
+      float sy = __fsub_rn(__fmul_rn(scale_h, static_cast<float>(y) + 0.5f), 0.5f);
+      float sx = __fsub_rn(__fmul_rn(scale_w, static_cast<float>(x) + 0.5f), 0.5f);
+      sy = sy < 0.0f ? 0.0f : sy;
+      sx = sx < 0.0f ? 0.0f : sx;
+      int y0 = static_cast<int>(sy);
+      int x0 = static_cast<int>(sx);
+      y0 = y0 > bh - 1 ? bh - 1 : y0;
+      x0 = x0 > bw - 1 ? bw - 1 : x0;
+      const int y1 = y0 + (y0 < bh - 1 ? 1 : 0);
+      const int x1 = x0 + (x0 < bw - 1 ? 1 : 0);
+      float ly1 = __fsub_rn(sy, static_cast<float>(y0));
+      float lx1 = __fsub_rn(sx, static_cast<float>(x0));
+      ly1 = fminf(fmaxf(ly1, 0.0f), 1.0f);
+      lx1 = fminf(fmaxf(lx1, 0.0f), 1.0f);
+      const float ly0 = __fsub_rn(1.0f, ly1);
+      const float lx0 = __fsub_rn(1.0f, lx1);
+      const uint8_t* base = frames + static_cast<size_t>(n) * H * W * 3;
+      const uint8_t* p00 = base + (static_cast<size_t>(top + y0) * W + (left + x0)) * 3;
+      const uint8_t* p01 = base + (static_cast<size_t>(top + y0) * W + (left + x1)) * 3;
+      const uint8_t* p10 = base + (static_cast<size_t>(top + y1) * W + (left + x0)) * 3;
+      const uint8_t* p11 = base + (static_cast<size_t>(top + y1) * W + (left + x1)) * 3;
+      float r[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v00 = static_cast<float>(__ldg(p00 + c));
+        const float v01 = static_cast<float>(__ldg(p01 + c));
+        const float v10 = static_cast<float>(__ldg(p10 + c));
+        const float v11 = static_cast<float>(__ldg(p11 + c));
+        const float t0 = __fadd_rn(__fmul_rn(v00, lx0), __fmul_rn(v01, lx1));
+        const float t1 = __fadd_rn(__fmul_rn(v10, lx0), __fmul_rn(v11, lx1));
+        const float v = __fadd_rn(__fmul_rn(t0, ly0), __fmul_rn(t1, ly1));
+        const float u8 = fminf(fmaxf(rintf(v), 0.0f), 255.0f);  // round half to even, uint8 range
+        const float x01 = __fdiv_rn(u8, 255.0f);
+        r[c] = __fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]);
+      }
+      const __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]);
+      const __nv_bfloat162 b = __floats2bfloat162_rn(r[2], 0.0f);
+      o.x = *reinterpret_cast<const uint32_t*>(&a);
+      o.y = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    reinterpret_cast<uint2*>(out)[idx] = o;
+  }
+}
+
+// Seam A repack: already-normalised fp32 NCHW [N,3,224,224] (src/preprocess_resnet_features.py:295) -> NHWC4p.
+__global__ void nchw_f32_to_stem_kernel(const float* __restrict__ x, int n_frames, __nv_bfloat16* __restrict__ out) {
+  const int total = n_frames * kImg * kStemWPad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int wp = idx % kStemWPad;
+    const int y = (idx / kStemWPad) % kImg;
+    const int n = idx / (kStemWPad * kImg);
+    uint2 o = make_uint2(0u, 0u);
+    const int xx = wp - kStemLeftPad;
+    if (xx >= 0 && xx < kImg) {
+      const size_t plane = static_cast<size_t>(kImg) * kImg;
+      const float* px = x + static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(y) * kImg + xx;
+      const __nv_bfloat162 a = __floats2bfloat162_rn(__ldg(px), __ldg(px + plane));
+      const __nv_bfloat162 b = __floats2bfloat162_rn(__ldg(px + 2 * plane), 0.0f);
+      o.x = *reinterpret_cast<const uint32_t*>(&a);
+      o.y = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    reinterpret_cast<uint2*>(out)[idx] = o;
+  }
+}
+
+// MaxPool2d(3, stride 2, pad 1) over NHWC bf16 (torchvision models/resnet.py:200); 8 channels per thread.
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, int n_frames, int Hin, int Win, int C,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int Ho = (Hin + 2 - 3) / 2 + 1;
+  const int Wo = (Win + 2 - 3) / 2 + 1;
+  const int cg = C / 8;
+  const long long total = static_cast<long long>(n_frames) * Ho * Wo * cg;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % cg);
+    const int qo = static_cast<int>((idx / cg) % Wo);
+    const int po = static_cast<int>((idx / (static_cast<long long>(cg) * Wo)) % Ho);
+    const int n = static_cast<int>(idx / (static_cast<long long>(cg) * Wo * Ho));
+    __nv_bfloat162 m[4];
+    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = ninf;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = 2 * po - 1 + dy;
+      if (y < 0 || y >= Hin) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = 2 * qo - 1 + dx;
+        if (x < 0 || x >= Win) continue;
+        const uint4 v =
+            __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(n) * Hin + y) * Win + x) * C) + g);
+        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], pv[j]);
+      }
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&m[0]);
+    o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&m[2]);
+    o.w = *reinterpret_cast<uint32_t*>(&m[3]);
+    reinterpret_cast<uint4*>(out)[idx] = o;
+  }
+}
+
+}  // namespace phdfxk

@@ -1,0 +1,184 @@
+"""B200Backbone — the object that takes the place of the reference's `backbone` (src/preprocess_resnet_features.py:207-209).
+
+Seam A (module-shaped):  feats = backbone(x).flatten(1).view(Bv, T, -1)   (:296) works verbatim:
+    backbone(x: cuda fp32 [N,3,224,224], ImageNet-normalised) -> cuda fp32 [N,2048,1,1]
+Seam B (fused, fast):    backbone.extract_u8(frames: cuda uint8 [N,H,W,3], boxes int32 [N,4] | None) -> [N,2048]
+    which also replaces the CPU crop/resize/normalise of src/dataset.py:141-152,242-245.
+
+All math runs in libphdfx.so (hand-written sm_100a kernels) on the current CUDA stream.  There is no fallback:
+constructing this object without a CUDA sm_100 device, or without the built extension, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .weights import Plan, build_plan
+
+
+class B200Backbone:
+    FEAT_DIM = _lib.FEAT_DIM
+
+    def __init__(self, backbone: nn.Module, device: "int | str | torch.device" = 0, max_frames: int = 1280):
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200Backbone needs a CUDA device (sm_100); this backend has no CPU fallback")
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise RuntimeError(f"B200Backbone cannot run on {dev}; this backend has no CPU fallback")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.max_frames = int(max_frames)
+        self.plan: Plan = build_plan(backbone)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.phdfx_create(C.byref(self._h), self.device.index, self.max_frames))
+        arr = (_lib.LayerDesc * len(self.plan.layers))(*self.plan.layers)
+        w, b = self.plan.weights, self.plan.bias
+        _lib.check(
+            self._lib.phdfx_load_weights(self._h, w.data_ptr(), w.numel(), b.data_ptr(), b.numel(), arr,
+                                         len(self.plan.layers)), self._h)
+
+    # ---- nn.Module-shaped surface the reference script touches (:209) ---------------------------------------
+    def to(self, *args, **kwargs):
+        return self
+
+    def eval(self):
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.phdfx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ------------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check_dev(self, t: torch.Tensor, name: str):
+        if not t.is_cuda or t.device.index != self.device.index:
+            raise RuntimeError(f"{name} must live on {self.device}, got {t.device}")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous")
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._lib.phdfx_last_launch_count(self._h))
+
+    # ---- Seam A ---------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """x: fp32 (or bf16/fp16, cast) NCHW [N,3,224,224] on the device -> fp32 [N,2048,1,1]."""
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, _lib.IMG, _lib.IMG):
+            raise RuntimeError(f"expected [N,3,224,224], got {tuple(x.shape)}")
+        x = x.to(torch.float32).contiguous()
+        self._check_dev(x, "x")
+        n = x.shape[0]
+        feats = torch.empty(n, self.FEAT_DIM, device=self.device, dtype=torch.float32)
+        launches = 0
+        with torch.cuda.device(self.device):
+            for i in range(0, n, self.max_frames):
+                m = min(self.max_frames, n - i)
+                st = self._stream()
+                _lib.check(self._lib.phdfx_nchw_f32_to_nhwc_bf16(self._h, x[i:i + m].data_ptr(), m, None, st),
+                           self._h)
+                launches += self.last_launch_count
+                _lib.check(self._lib.phdfx_forward(self._h, None, m, feats[i:i + m].data_ptr(), st), self._h)
+                launches += self.last_launch_count
+        self.launches = launches
+        return feats.view(n, self.FEAT_DIM, 1, 1)
+
+    forward = __call__
+
+    # ---- Seam B ---------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def extract_u8(self, frames: torch.Tensor, boxes: Optional[torch.Tensor] = None, flip_w: bool = False,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames: uint8 [N,H,W,3] on the device; boxes: int32 [N,4] (top,left,h,w) or None -> fp32 [N,2048]."""
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+            raise RuntimeError(f"expected uint8 [N,H,W,3], got {frames.dtype} {tuple(frames.shape)}")
+        self._check_dev(frames, "frames")
+        n, H, W, _ = frames.shape
+        if boxes is not None:
+            if boxes.dtype != torch.int32 or tuple(boxes.shape) != (n, 4):
+                raise RuntimeError("boxes must be int32 [N,4] (top, left, h, w)")
+            self._check_dev(boxes, "boxes")
+        feats = out if out is not None else torch.empty(n, self.FEAT_DIM, device=self.device, dtype=torch.float32)
+        if out is not None:
+            if out.dtype != torch.float32 or tuple(out.shape) != (n, self.FEAT_DIM):
+                raise RuntimeError("out must be fp32 [N,2048]")
+            self._check_dev(out, "out")
+        launches = 0
+        with torch.cuda.device(self.device):
+            for i in range(0, n, self.max_frames):
+                m = min(self.max_frames, n - i)
+                bp = boxes[i:i + m].data_ptr() if boxes is not None else None
+                _lib.check(
+                    self._lib.phdfx_extract_u8(self._h, frames[i:i + m].data_ptr(), m, H, W, bp, int(flip_w),
+                                               feats[i:i + m].data_ptr(), self._stream()), self._h)
+                launches += self.last_launch_count
+        self.launches = launches
+        return feats
+
+    @torch.no_grad()
+    def preprocess_u8(self, frames: torch.Tensor, boxes: Optional[torch.Tensor] = None,
+                      flip_w: bool = False) -> torch.Tensor:
+        """K1 alone: uint8 [N,H,W,3] -> bf16 NHWC4p [N,224,232,4] (the trunk's input layout)."""
+        self._check_dev(frames, "frames")
+        n, H, W, _ = frames.shape
+        out = torch.empty(n, _lib.IMG, _lib.IN_WPAD, _lib.IN_CPAD, device=self.device, dtype=torch.bfloat16)
+        with torch.cuda.device(self.device):
+            for i in range(0, n, self.max_frames):
+                m = min(self.max_frames, n - i)
+                bp = boxes[i:i + m].data_ptr() if boxes is not None else None
+                _lib.check(
+                    self._lib.phdfx_preprocess_u8(self._h, frames[i:i + m].data_ptr(), m, H, W, bp, int(flip_w),
+                                                  out[i:i + m].data_ptr(), self._stream()), self._h)
+        return out
+
+    @torch.no_grad()
+    def forward_nhwc4p(self, x: torch.Tensor) -> torch.Tensor:
+        """Trunk on an explicit NHWC4p bf16 input [N,224,232,4] -> fp32 [N,2048]."""
+        self._check_dev(x, "x")
+        n = x.shape[0]
+        if x.dtype != torch.bfloat16 or tuple(x.shape[1:]) != (_lib.IMG, _lib.IN_WPAD, _lib.IN_CPAD):
+            raise RuntimeError("expected bf16 [N,224,232,4]")
+        if n > self.max_frames:
+            raise RuntimeError(f"n = {n} > max_frames = {self.max_frames}")
+        feats = torch.empty(n, self.FEAT_DIM, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.phdfx_forward(self._h, x.data_ptr(), n, feats.data_ptr(), self._stream()), self._h)
+        return feats
+
+    # ---- per-layer hook --------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run_layer(self, layer_id: int, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Run one entry of the execution list on explicit tensors (NHWC bf16; NHWC4p for the stem)."""
+        L = self.plan.layers[layer_id]
+        n = x.shape[0]
+        self._check_dev(x, "x")
+        if L.kind == _lib.PHDFX_MAXPOOL:
+            ho = (L.hin + 2 - 3) // 2 + 1
+            out = torch.empty(n, ho, ho, L.cout, device=self.device, dtype=torch.bfloat16)
+        else:
+            ho = (L.hin + 2 * L.pad - L.r) // L.stride + 1
+            if L.gap:
+                out = torch.empty(n, L.cout, device=self.device, dtype=torch.float32)
+            else:
+                out = torch.empty(n, ho, ho, L.cout, device=self.device, dtype=torch.bfloat16)
+        rp = None
+        if residual is not None:
+            self._check_dev(residual, "residual")
+            rp = residual.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.phdfx_run_layer(self._h, layer_id, x.data_ptr(), rp, out.data_ptr(), n,
+                                                 self._stream()), self._h)
+        return out

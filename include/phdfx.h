@@ -1,0 +1,111 @@
+/* phdfx.h — C ABI of the B200-native ResNet-50 frame-feature extractor (libphdfx.so).
+ *
+ * The reference (ferreiraluisa/implementation-phd-lab-vision) has no FFI: its seam is one Python callable,
+ *     feats = backbone(x).flatten(1).view(Bv, T, -1)          src/preprocess_resnet_features.py:296
+ * fed by the CPU crop/resize/normalise in src/dataset.py:141-152,242-245.  These entry points are what a binding for
+ * that seam calls (INTEGRATION.md shows the ctypes stub).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative phdfx_status otherwise; the message is phdfx_last_error().
+ *   - all d_* pointers are DEVICE pointers owned by the caller and must stay alive until the stream work is done.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  No call synchronises the device;
+ *     every call is CUDA-graph capturable.
+ *   - a handle is bound to one device and is not thread-safe.  There is NO CPU fallback: creation fails on a device
+ *     that is not compute capability 10.x.
+ */
+#ifndef PHDFX_H_
+#define PHDFX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHDFX_VERSION 100 /* major*100 + minor */
+
+typedef struct phdfx phdfx_t;
+
+typedef enum phdfx_status {
+  PHDFX_OK = 0,
+  PHDFX_ERR_INVALID = -1,   /* bad argument / shape / n > max_frames */
+  PHDFX_ERR_ARCH = -2,      /* device is not sm_100 */
+  PHDFX_ERR_CUDA = -3,      /* CUDA runtime / driver error */
+  PHDFX_ERR_STATE = -4,     /* weights not loaded */
+} phdfx_status;
+
+typedef enum phdfx_layer_kind {
+  PHDFX_CONV = 0,    /* implicit-GEMM conv: 1x1 or 3x3, stride 1 or 2, Cin % 64 == 0, Cout % 64 == 0 */
+  PHDFX_STEM = 1,    /* 7x7 stride-2 pad-3 conv, 3 -> 64 channels, on the NHWC4p input layout */
+  PHDFX_MAXPOOL = 2, /* 3x3 stride-2 pad-1 max-pool */
+} phdfx_layer_kind;
+
+/* One entry of the execution list handed to phdfx_load_weights.  Mirrors one conv(+folded BN)(+ReLU)(+residual)
+ * of torchvision's ResNet (models/resnet.py:143-163, :268-271).  Buffers are ids into the library-owned activation
+ * arena; buffer 0 is the network input in NHWC4p layout. */
+typedef struct phdfx_layer_desc {
+  int32_t kind;            /* phdfx_layer_kind */
+  int32_t cin, cout;
+  int32_t r, s;            /* filter height / width */
+  int32_t stride, pad;
+  int32_t hin, win;        /* input spatial size */
+  int32_t relu;            /* ReLU at the end of the epilogue */
+  int32_t in_buf, out_buf; /* arena buffer ids */
+  int32_t res_buf;         /* residual added before ReLU; -1 = none */
+  int32_t gap;             /* 1: fuse AdaptiveAvgPool2d(1) (resnet.py:278): emit fp32 [n, cout] features */
+  int64_t w_off;           /* element offset of this layer's packed weights [cout][r][s][cin] (stem: [7][64][32]) */
+  int64_t b_off;           /* element offset of this layer's folded-BN bias [cout] */
+} phdfx_layer_desc;
+
+/* Geometry of the NHWC4p network-input layout: bf16 [n][224][232][4]; pixel column = w + 4, channel 3 = 0. */
+#define PHDFX_IMG 224
+#define PHDFX_IN_WPAD 232
+#define PHDFX_IN_LPAD 4
+#define PHDFX_IN_CPAD 4
+#define PHDFX_FEAT_DIM 2048
+
+int phdfx_version(void);
+const char* phdfx_last_error(const phdfx_t* h); /* h may be NULL: last error of the calling thread */
+
+/* Replaces `backbone.to(device).eval()` (preprocess_resnet_features.py:207-209): binds a device, sizes the arena. */
+int phdfx_create(phdfx_t** h, int device_ordinal, int max_frames);
+int phdfx_destroy(phdfx_t* h);
+
+/* Host pointers.  packed_bf16: n_weights bf16 values; bias_f32: n_bias floats; layers: execution list.
+ * BN folding and packing are done by the host (phdfx/weights.py); the library copies to the device and owns them. */
+int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, const float* bias_f32,
+                       int64_t n_bias, const phdfx_layer_desc* layers, int n_layers);
+
+/* K1 — replaces src/dataset.py:141-152 (_crop_and_resize_video_uint8) + :242-245 (Normalize).
+ * d_frames_hwc: uint8 [n][H][W][3]; d_boxes: int32 [n][4] (top,left,h,w) or NULL (= whole frame);
+ * flip_w != 0 mirrors the output horizontally (the reference's hflip variant, dataset.py:158-186);
+ * d_out_nhwc4p: bf16 NHWC4p or NULL (= the arena's input buffer). */
+int phdfx_preprocess_u8(phdfx_t* h, const uint8_t* d_frames_hwc, int n, int H, int W, const int32_t* d_boxes,
+                        int flip_w, void* d_out_nhwc4p, void* stream);
+
+/* Seam A repack: fp32 NCHW [n,3,224,224], already normalised (the tensor the reference feeds to backbone(), :295)
+ * -> NHWC4p bf16 (NULL = arena input buffer). */
+int phdfx_nchw_f32_to_nhwc_bf16(phdfx_t* h, const float* d_x_nchw, int n, void* d_out_nhwc4p, void* stream);
+
+/* The trunk — replaces backbone(x).flatten(1) (:296).  d_in_nhwc4p NULL = arena input buffer.
+ * d_feats: fp32 [n][2048]. */
+int phdfx_forward(phdfx_t* h, const void* d_in_nhwc4p, int n, float* d_feats, void* stream);
+
+/* Seam B: preprocess + trunk. */
+int phdfx_extract_u8(phdfx_t* h, const uint8_t* d_frames_hwc, int n, int H, int W, const int32_t* d_boxes,
+                     int flip_w, float* d_feats, void* stream);
+
+/* Per-layer hook (parity tests, ncu, per-layer benchmark).  d_in / d_residual / d_out use the layer's own
+ * layouts: NHWC bf16 activations (NHWC4p for the stem input); for a gap layer d_out is fp32 [n][cout]. */
+int phdfx_run_layer(phdfx_t* h, int layer_id, const void* d_in, const void* d_residual, void* d_out, int n,
+                    void* stream);
+
+int phdfx_layer_count(const phdfx_t* h);
+int phdfx_layer_info(const phdfx_t* h, int layer_id, phdfx_layer_desc* out);
+/* Number of kernels the last phdfx_forward / phdfx_extract_u8 / phdfx_preprocess_u8 call launched. */
+int phdfx_last_launch_count(const phdfx_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHDFX_H_ */
