@@ -18,8 +18,10 @@ constexpr int kStemLeftPad = 4;
 //   crop [top:top+h, left:left+w] -> F.resize(224, bilinear, antialias=False) evaluated in fp32 and ROUNDED
 //   half-to-even back to uint8 (torchvision transforms/_functional_tensor.py:462-472,536-540) -> /255 ->
 //   (x - mean) / std  (fp32) -> bf16.
-// ATen's bilinear (align_corners=False): src = max(0, scale*(dst+0.5)-0.5), scale = in/out in fp32;
-//   value = wh0*(ww0*v00 + ww1*v01) + wh1*(ww0*v10 + ww1*v11), each product/sum rounded to fp32 (no FMA).
+// ATen's bilinear (align_corners=False), in the exact fp32 operation order of the kernel the reference's
+// DataLoader workers run (1 thread -> channels-last kernel; pinned bit-for-bit by oracle/preprocess_ref.py):
+//   src = max(0, fma(scale, dst+0.5, -0.5)), scale = in/out;  wij = lam_h_i * lam_w_j;
+//   value = fma(w11,v11, fma(w10,v10, fma(w00,v00, w01*v01))).
 __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                                      const int32_t* __restrict__ boxes, int flip_w, __nv_bfloat16* __restrict__ out) {
   const int total = n_frames * kImg * kStemWPad;
@@ -42,8 +44,8 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_f
       }
       const float scale_h = __fdiv_rn(static_cast<float>(bh), static_cast<float>(kImg));
       const float scale_w = __fdiv_rn(static_cast<float>(bw), static_cast<float>(kImg));
-      float sy = __fsub_rn(__fmul_rn(scale_h, static_cast<float>(y) + 0.5f), 0.5f);
-      float sx = __fsub_rn(__fmul_rn(scale_w, static_cast<float>(x) + 0.5f), 0.5f);
+      float sy = __fmaf_rn(scale_h, static_cast<float>(y) + 0.5f, -0.5f);
+      float sx = __fmaf_rn(scale_w, static_cast<float>(x) + 0.5f, -0.5f);
       sy = sy < 0.0f ? 0.0f : sy;
       sx = sx < 0.0f ? 0.0f : sx;
       int y0 = static_cast<int>(sy);
@@ -63,6 +65,8 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_f
       const uint8_t* p01 = base + (static_cast<size_t>(top + y0) * W + (left + x1)) * 3;
       const uint8_t* p10 = base + (static_cast<size_t>(top + y1) * W + (left + x0)) * 3;
       const uint8_t* p11 = base + (static_cast<size_t>(top + y1) * W + (left + x1)) * 3;
+      const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1);
+      const float w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
       float r[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -70,9 +74,7 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_f
         const float v01 = static_cast<float>(__ldg(p01 + c));
         const float v10 = static_cast<float>(__ldg(p10 + c));
         const float v11 = static_cast<float>(__ldg(p11 + c));
-        const float t0 = __fadd_rn(__fmul_rn(v00, lx0), __fmul_rn(v01, lx1));
-        const float t1 = __fadd_rn(__fmul_rn(v10, lx0), __fmul_rn(v11, lx1));
-        const float v = __fadd_rn(__fmul_rn(t0, ly0), __fmul_rn(t1, ly1));
+        const float v = __fmaf_rn(w11, v11, __fmaf_rn(w10, v10, __fmaf_rn(w00, v00, __fmul_rn(w01, v01))));
         const float u8 = fminf(fmaxf(rintf(v), 0.0f), 255.0f);  // round half to even, uint8 range
         const float x01 = __fdiv_rn(u8, 255.0f);
         r[c] = __fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]);

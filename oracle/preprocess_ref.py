@@ -24,12 +24,22 @@ IMAGENET_MEAN = np.array([0.485, 0.456, 0.406], dtype=np.float32)
 IMAGENET_STD = np.array([0.229, 0.224, 0.225], dtype=np.float32)
 
 
+def _fma(a, b, c):
+    """fp32 fused multiply-add: the product of two fp32 values is exact in fp64, one rounding to fp32 follows."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def _mul(a, b):
+    return (np.asarray(a, np.float32) * np.asarray(b, np.float32)).astype(np.float32)
+
+
 def _src_index(out_size: int, in_size: int):
-    """ATen area_pixel_compute_source_index (align_corners=False, no explicit scale) + guard_index_and_lambda."""
+    """ATen area_pixel_compute_source_index (align_corners=False, no explicit scale) + guard_index_and_lambda.
+    The shipped ATen binary contracts scale*(dst+0.5)-0.5 into one FMA (established empirically, see header)."""
     f32 = np.float32
     scale = f32(in_size) / f32(out_size)
     dst = np.arange(out_size, dtype=np.float32)
-    src = scale * (dst + f32(0.5)) - f32(0.5)
+    src = _fma(np.full_like(dst, scale), dst + f32(0.5), np.full_like(dst, f32(-0.5)))
     src = np.where(src < 0, f32(0), src).astype(np.float32)
     i0 = np.minimum(np.floor(src).astype(np.int64), in_size - 1)
     lam1 = np.clip(src - i0.astype(np.float32), f32(0), f32(1)).astype(np.float32)
@@ -38,33 +48,49 @@ def _src_index(out_size: int, in_size: int):
     return i0, i1, lam0, lam1
 
 
-def crop_resize_u8(frames_u8: np.ndarray, box, out_size: int = 224) -> np.ndarray:
+def crop_resize_u8(frames_u8: np.ndarray, box, out_size: int = 224, aten_path: str = "worker") -> np.ndarray:
     """frames_u8: (T,H,W,3) uint8; box = (top, left, h, w) -> (T,3,out,out) uint8 (the rounded resize result).
 
     dataset.py:141-148.  If the crop already is out_size x out_size, F.resize returns it untouched
     (torchvision transforms/functional.py:470-471); the arithmetic below reproduces that exactly (lambda = 0).
+
+    torch 2.11's CPU upsample_bilinear2d picks one of two kernels for 3-channel fp32 input
+    (ATen UpSampleKernel.cpp, upsample_bilinear2d_kernel_impl_float), which differ in the last ulp:
+      aten_path="worker"  : get_num_threads() == 1 — what the reference's DataLoader workers run
+                            (src/preprocess_resnet_features.py:195-204, num_workers=8): the channels-last kernel,
+                            v = fma(w11,v11, fma(w10,v10, fma(w00,v00, w01*v01))),  wij = lam_h_i * lam_w_j
+      aten_path="generic" : multi-threaded caller (num_workers=0): the separable generic kernel,
+                            t_i = fma(v_i0, lw0, v_i1*lw1);  v = fma(t_0, lh0, t_1*lh1)
+    Both orders were established by bit-exact comparison with the installed ATen (oracle/make_golden.py pins them).
+    The CUDA kernel implements "worker".
     """
     top, left, hh, ww = (int(v) for v in box)
     crop = frames_u8[:, top:top + hh, left:left + ww, :].astype(np.float32)  # (T,h,w,3)
     y0, y1, ly0, ly1 = _src_index(out_size, hh)
     x0, x1, lx0, lx1 = _src_index(out_size, ww)
-    # ATen cpu generic kernel order: inner (W) interpolation first, then H; every product and sum rounded to fp32.
     r0 = crop[:, y0]  # (T,out,w,3)
     r1 = crop[:, y1]
-    lx0b = lx0[None, None, :, None]
-    lx1b = lx1[None, None, :, None]
-    t0 = (r0[:, :, x0] * lx0b).astype(np.float32) + (r0[:, :, x1] * lx1b).astype(np.float32)
-    t1 = (r1[:, :, x0] * lx0b).astype(np.float32) + (r1[:, :, x1] * lx1b).astype(np.float32)
-    ly0b = ly0[None, :, None, None]
-    ly1b = ly1[None, :, None, None]
-    v = (t0 * ly0b).astype(np.float32) + (t1 * ly1b).astype(np.float32)
+    v00, v01, v10, v11 = r0[:, :, x0], r0[:, :, x1], r1[:, :, x0], r1[:, :, x1]
+    a = lx0[None, None, :, None]
+    b = lx1[None, None, :, None]
+    c = ly0[None, :, None, None]
+    d = ly1[None, :, None, None]
+    if aten_path == "worker":
+        w00, w01, w10, w11 = _mul(c, a), _mul(c, b), _mul(d, a), _mul(d, b)
+        v = _fma(w11, v11, _fma(w10, v10, _fma(w00, v00, _mul(w01, v01))))
+    elif aten_path == "generic":
+        t0 = _fma(v00, a, _mul(v01, b))
+        t1 = _fma(v10, a, _mul(v11, b))
+        v = _fma(t0, c, _mul(t1, d))
+    else:
+        raise ValueError(aten_path)
     u8 = np.clip(np.rint(v), 0, 255).astype(np.uint8)  # torch.round = half to even, like np.rint
     return np.ascontiguousarray(u8.transpose(0, 3, 1, 2))
 
 
-def crop_resize_normalize(frames_u8: np.ndarray, box, out_size: int = 224) -> np.ndarray:
+def crop_resize_normalize(frames_u8: np.ndarray, box, out_size: int = 224, aten_path: str = "worker") -> np.ndarray:
     """(T,H,W,3) uint8 -> (T,3,out,out) fp32, ImageNet-normalised: dataset.py:141-152 then :429."""
-    u8 = crop_resize_u8(frames_u8, box, out_size)
+    u8 = crop_resize_u8(frames_u8, box, out_size, aten_path)
     x = u8.astype(np.float32) / np.float32(255.0)
     x = (x - IMAGENET_MEAN[None, :, None, None]) / IMAGENET_STD[None, :, None, None]
     return x.astype(np.float32)

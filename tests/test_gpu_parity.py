@@ -1,0 +1,299 @@
+"""Parity tests proper (run on the B200 box with -m gpu).  Everything goes through the C ABI (libphdfx.so via
+phdfx.B200Backbone); the checker is the oracle (oracle/*.py, oracle/resnet50_ref.c) and the committed golden vectors
+generated from the reference's own arithmetic.  Nothing here reads /root/reference.
+
+Tolerance (BASELINE.json north_star): per frame  max|got - ref| / max|ref| <= 2e-2  and  cosine >= 0.9999  for the
+bf16 trunk against the fp32 reference; bit-exact for the uint8 resize and the bf16 NHWC4p bytes K1 writes.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import phdfx
+import preprocess_ref as P
+import resnet50_ref as R
+
+pytestmark = pytest.mark.gpu
+
+NORM_TOL = 2e-2
+COS_TOL = 0.9999
+
+
+def frame_errors(got: np.ndarray, ref: np.ndarray):
+    err = np.abs(got - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    return err, cos
+
+
+@pytest.fixture(scope="module")
+def backbone():
+    return R.seeded_backbone()
+
+
+@pytest.fixture(scope="module")
+def eng(backbone):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    e = phdfx.B200Backbone(backbone, device=0, max_frames=32)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "trunk_golden.npz"))
+
+
+# ------------------------------------------------------------------------------------------------ K1 preprocess
+def _pre_cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "preprocess_golden.npz"))
+    i = 0
+    while f"case{i}_meta" in g:
+        n, H, W, top, left, hh, ww, seed = (int(v) for v in g[f"case{i}_meta"])
+        yield g, i, R.seeded_frames(n, H, W, seed), (top, left, hh, ww)
+        i += 1
+
+
+def test_preprocess_bit_exact_vs_reference_golden(eng, golden_dir):
+    """K1 output bytes == bf16(normalise(reference resize golden)) — bit-exact, incl. padding columns/channel."""
+    for g, i, frames, box in _pre_cases(golden_dir):
+        n = frames.shape[0]
+        boxes = torch.tensor([box] * n, dtype=torch.int32, device="cuda")
+        got = eng.preprocess_u8(torch.from_numpy(frames).cuda(), boxes)
+        u8 = g[f"case{i}_u8_worker"].astype(np.float32)
+        x = (u8 / np.float32(255.0) - P.IMAGENET_MEAN[None, :, None, None]) / P.IMAGENET_STD[None, :, None, None]
+        want = P.to_nhwc4p_bf16_bits(x.astype(np.float32))
+        got_bits = got.view(torch.int16).cpu().numpy().view(np.uint16)
+        assert np.array_equal(got_bits, want), f"case {i} box {box}: {(got_bits != want).sum()} differing values"
+
+
+def test_preprocess_matches_oracle_on_ragged_boxes(eng):
+    """Per-frame boxes of different sizes/positions in one call (the reference uses one box per clip)."""
+    frames = R.seeded_frames(5, 333, 417, 21)
+    boxes = [(0, 0, 333, 333), (10, 100, 224, 224), (50, 60, 97, 97), (332, 416, 1, 1), (3, 5, 301, 301)]
+    got = eng.preprocess_u8(torch.from_numpy(frames).cuda(), torch.tensor(boxes, dtype=torch.int32, device="cuda"))
+    got_bits = got.view(torch.int16).cpu().numpy().view(np.uint16)
+    for k, box in enumerate(boxes):
+        want = P.to_nhwc4p_bf16_bits(P.crop_resize_normalize(frames[k:k + 1], box))
+        assert np.array_equal(got_bits[k:k + 1], want), f"frame {k} box {box}"
+
+
+def test_preprocess_hflip(eng):
+    """flip_w mirrors the resized clip (src/dataset.py:166), bit-exact."""
+    frames = R.seeded_frames(2, 260, 300, 22)
+    box = (7, 9, 240, 240)
+    boxes = torch.tensor([box] * 2, dtype=torch.int32, device="cuda")
+    got = eng.preprocess_u8(torch.from_numpy(frames).cuda(), boxes, flip_w=True)
+    want = P.to_nhwc4p_bf16_bits(P.hflip(P.crop_resize_normalize(frames, box)))
+    assert np.array_equal(got.view(torch.int16).cpu().numpy().view(np.uint16), want)
+
+
+def test_preprocess_whole_frame_when_no_boxes(eng):
+    frames = R.seeded_frames(2, 224, 224, 23)
+    got = eng.preprocess_u8(torch.from_numpy(frames).cuda(), None)
+    want = P.to_nhwc4p_bf16_bits(P.crop_resize_normalize(frames, (0, 0, 224, 224)))
+    assert np.array_equal(got.view(torch.int16).cpu().numpy().view(np.uint16), want)
+
+
+# ------------------------------------------------------------------------------------------------ per-layer
+def _layer_modules(bb):
+    out = {"conv1": (bb[0], bb[1])}
+    for li in range(4):
+        for bi, blk in enumerate(bb[4 + li]):
+            p = f"layer{li + 1}.{bi}"
+            out[p + ".conv1"] = (blk.conv1, blk.bn1)
+            out[p + ".conv2"] = (blk.conv2, blk.bn2)
+            out[p + ".conv3"] = (blk.conv3, blk.bn3)
+            if blk.downsample is not None:
+                out[p + ".downsample"] = (blk.downsample[0], blk.downsample[1])
+    return out
+
+
+def _unique_layers(plan):
+    seen = set()
+    for i, (name, L) in enumerate(zip(plan.names, plan.layers)):
+        key = (L.kind, L.cin, L.cout, L.r, L.stride, L.hin, L.res_buf >= 0, L.relu, L.gap)
+        if key not in seen:
+            seen.add(key)
+            yield i, name, L
+
+
+@pytest.mark.parametrize("n", [1, 5])
+def test_every_layer_shape_vs_fp32_torch(eng, backbone, n):
+    """Each of the 24 unique GEMM shapes (+ stem, maxpool, gap), on the same bf16-rounded operands, vs fp32 PyTorch.
+    n = 1 and 5 exercise the partial last M tile and the odd-frame tail of the fused average pool."""
+    mods = _layer_modules(backbone)
+    g = torch.Generator(device="cuda").manual_seed(100 + n)
+    checked = 0
+    for i, name, L in _unique_layers(eng.plan):
+        if L.kind == 2:
+            x = torch.relu(torch.randn(n, L.hin, L.win, L.cin, device="cuda", generator=g)).to(torch.bfloat16)
+            got = eng.run_layer(i, x)
+            ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+            assert torch.equal(got.float(), ref), name
+            checked += 1
+            continue
+        conv, bn = mods[name]
+        w, b = phdfx.fold_conv_bn(conv, bn)
+        w = w.to(torch.bfloat16).float().cuda()
+        if L.kind == 1:
+            x_nchw = torch.randn(n, 3, 224, 224, device="cuda", generator=g)
+            x_in = torch.zeros(n, 224, 232, 4, device="cuda", dtype=torch.bfloat16)
+            x_in[:, :, 4:228, :3] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+            x_ref = x_nchw.to(torch.bfloat16).float()
+        else:
+            x_in = torch.randn(n, L.hin, L.win, L.cin, device="cuda", generator=g).to(torch.bfloat16)
+            x_ref = x_in.float().permute(0, 3, 1, 2)
+        ho = (L.hin + 2 * L.pad - L.r) // L.stride + 1
+        res = None
+        if L.res_buf >= 0:
+            res = torch.randn(n, ho, ho, L.cout, device="cuda", generator=g).to(torch.bfloat16)
+        got = eng.run_layer(i, x_in, res)
+        ref = F.conv2d(x_ref, w, b.cuda(), stride=conv.stride, padding=conv.padding)
+        if res is not None:
+            ref = ref + res.float().permute(0, 3, 1, 2)
+        if L.relu:
+            ref = torch.relu(ref)
+        if L.gap:
+            ref = ref.mean(dim=(2, 3))
+            tol = 1e-4  # fp32 in, fp32 out
+        else:
+            ref = ref.permute(0, 2, 3, 1)
+            tol = 6e-3  # one bf16 rounding of the output
+        err = (got.float() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < tol, f"{name}: normalised error {err}"
+        checked += 1
+    assert checked >= 26
+
+
+# ------------------------------------------------------------------------------------------------ whole path
+def test_config1_features_vs_reference_golden(eng, golden):
+    """BASELINE config 1 stand-in: 16 frames (2 clips x 8), 1002x1000 uint8, box (100,200,517,517), Seam B
+    (uint8 in, features out) against features the reference's own CPU fp32 path produced."""
+    n, H, W, top, left, hh, ww, seed = (int(v) for v in golden["meta"][:8])
+    frames = torch.from_numpy(R.seeded_frames(n, H, W, seed)).cuda()
+    boxes = torch.tensor([(top, left, hh, ww)] * n, dtype=torch.int32, device="cuda")
+    feats = eng.extract_u8(frames, boxes)
+    # the reference's reshape at :296
+    clips = feats.view(2, 8, -1)
+    assert clips.shape == (2, 8, 2048)
+    err, cos = frame_errors(feats.cpu().numpy(), golden["feats"])
+    assert err.max() <= NORM_TOL and cos.min() >= COS_TOL, (err, cos)
+
+
+def test_identity_size_input_vs_golden(eng, golden):
+    frames = torch.from_numpy(R.seeded_frames(4, 224, 224, 2)).cuda()
+    feats = eng.extract_u8(frames, None).cpu().numpy()
+    err, cos = frame_errors(feats, golden["feats_identity"])
+    assert err.max() <= NORM_TOL and cos.min() >= COS_TOL, (err, cos)
+
+
+def test_seam_a_module_call_vs_c_oracle(eng, backbone):
+    """Seam A: backbone(x).flatten(1).view(Bv, T, -1) verbatim (src/preprocess_resnet_features.py:295-296), checked
+    against the plain-C oracle on 2 frames."""
+    frames = R.seeded_frames(2, 300, 280, 5)
+    x = P.crop_resize_normalize(frames, (20, 30, 217, 217))
+    v_video = torch.from_numpy(x).view(1, 2, 3, 224, 224).cuda()
+    Bv, T, C, H, W = v_video.shape
+    xx = v_video.view(Bv * T, C, H, W).contiguous()
+    out = eng(xx)
+    assert out.shape == (2, 2048, 1, 1) and out.dtype == torch.float32
+    feats = out.flatten(1).view(Bv, T, -1)
+    ref = R.features(x, R.param_list(backbone))
+    err, cos = frame_errors(feats.view(2, -1).cpu().numpy(), ref)
+    assert err.max() <= NORM_TOL and cos.min() >= COS_TOL, (err, cos)
+
+
+def test_seam_a_equals_seam_b(eng):
+    """Normalised-fp32 entry and uint8 entry agree bit-for-bit (both feed the same bf16 NHWC4p bytes)."""
+    frames = R.seeded_frames(3, 240, 250, 6)
+    box = (4, 6, 230, 230)
+    a = eng(torch.from_numpy(P.crop_resize_normalize(frames, box)).cuda()).flatten(1)
+    b = eng.extract_u8(torch.from_numpy(frames).cuda(), torch.tensor([box] * 3, dtype=torch.int32, device="cuda"))
+    assert torch.equal(a, b)
+
+
+def test_external_input_buffer_equals_arena(eng):
+    frames = torch.from_numpy(R.seeded_frames(3, 224, 224, 7)).cuda()
+    x4 = eng.preprocess_u8(frames, None)
+    assert torch.equal(eng.forward_nhwc4p(x4), eng.extract_u8(frames, None))
+
+
+# ------------------------------------------------------------------------------------------------ edge cases / properties
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 32])
+def test_batch_sizes_and_frame_independence(eng, n):
+    """Frames are independent (BN in eval mode): features of a frame do not depend on batch size or position —
+    bit-exact, since every output row is produced by the same MMA / reduction order wherever it sits in a tile."""
+    frames = torch.from_numpy(R.seeded_frames(32, 224, 224, 8)).cuda()
+    full = eng.extract_u8(frames, None)
+    sub = eng.extract_u8(frames[:n].contiguous(), None)
+    assert torch.equal(sub, full[:n])
+    perm = torch.randperm(32, generator=torch.Generator().manual_seed(n)).cuda()
+    permuted = eng.extract_u8(frames[perm].contiguous(), None)
+    assert torch.equal(permuted, full[perm])
+
+
+def test_chunking_over_max_frames(eng):
+    frames = torch.from_numpy(R.seeded_frames(70, 224, 224, 9)).cuda()  # max_frames = 32 -> 32 + 32 + 6
+    feats = eng.extract_u8(frames, None)
+    again = torch.cat([eng.extract_u8(frames[i:i + 10].contiguous(), None) for i in range(0, 70, 10)])
+    assert torch.equal(feats, again)
+    assert not torch.isnan(feats).any() and feats.min() >= 0  # post-ReLU mean
+
+
+def test_deterministic(eng):
+    frames = torch.from_numpy(R.seeded_frames(9, 224, 224, 10)).cuda()
+    a = eng.extract_u8(frames, None).clone()
+    b = eng.extract_u8(frames, None)
+    assert torch.equal(a, b)
+
+
+def test_time_reverse_variant_is_a_permutation(eng):
+    """The reference's `trev` augmentation (src/dataset.py:201-207) reverses the clip in time; frames being
+    independent, its features are exactly the reversed `orig` features."""
+    frames = torch.from_numpy(R.seeded_frames(8, 224, 224, 11)).cuda()
+    orig = eng.extract_u8(frames, None)
+    trev = eng.extract_u8(torch.flip(frames, dims=[0]).contiguous(), None)
+    assert torch.equal(trev, torch.flip(orig, dims=[0]))
+
+
+def test_streaming_host_api(eng):
+    """Host-buffer front door: pinned H2D -> K1 -> trunk -> D2H, double-buffered; equals the device-resident path."""
+    frames = R.seeded_frames(50, 224, 224, 12)
+    box = (0, 0, 224, 224)
+    se = phdfx.StreamingExtractor(eng, batch=16)
+    host = se(torch.from_numpy(frames), torch.tensor([box] * 50))
+    dev = eng.extract_u8(torch.from_numpy(frames).cuda(), None).cpu()
+    assert host.shape == (50, 2048) and torch.equal(host, dev)
+    assert se.h2d_bytes == 50 * 224 * 224 * 3 + 50 * 16 and se.d2h_bytes == 50 * 2048 * 4
+    se16 = phdfx.StreamingExtractor(eng, batch=16, save_fp16=True)  # --save-fp16 (:146)
+    assert torch.equal(se16(torch.from_numpy(frames)), dev.to(torch.float16))
+
+
+def test_errors_are_loud(eng):
+    with pytest.raises(RuntimeError):
+        eng(torch.zeros(2, 3, 200, 200, device="cuda"))
+    with pytest.raises(RuntimeError):
+        eng.extract_u8(torch.zeros(2, 224, 224, 3, dtype=torch.uint8), None)  # host tensor
+    with pytest.raises(RuntimeError):
+        eng.forward_nhwc4p(torch.zeros(33, 224, 232, 4, device="cuda", dtype=torch.bfloat16))  # > max_frames
+    with pytest.raises(RuntimeError, match="residual"):
+        i = eng.plan.names.index("layer1.0.conv3")
+        eng.run_layer(i, torch.zeros(1, 56, 56, 64, device="cuda", dtype=torch.bfloat16), None)
+
+
+def test_full_batch_256_properties():
+    """BASELINE config 2 size (batch 256): too big for the CPU oracle, so check size-independent properties —
+    equality with the same frames pushed through in small batches, and the native library is what ran."""
+    bb = R.seeded_backbone()
+    e = phdfx.B200Backbone(bb, device=0, max_frames=256)
+    frames = torch.from_numpy(R.seeded_frames(256, 224, 224, 13)).cuda()
+    big = e.extract_u8(frames, None)
+    assert e.launches == 55  # K1 + 53 convs + maxpool, all ours
+    small = torch.cat([e.extract_u8(frames[i:i + 37].contiguous(), None) for i in range(0, 256, 37)])
+    assert torch.equal(big, small)
+    assert torch.isfinite(big).all()
+    e.close()

@@ -1,0 +1,109 @@
+"""Host logic: BN folding, weight packing, execution list (phdfx/weights.py)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import phdfx
+import resnet50_ref as R
+
+
+@pytest.fixture(scope="module")
+def backbone():
+    return R.seeded_backbone()
+
+
+@pytest.fixture(scope="module")
+def plan(backbone):
+    return phdfx.build_plan(backbone)
+
+
+def test_fold_is_exact_in_fp32(backbone):
+    blk = backbone[5][0]  # layer2.0 (has stride + downsample)
+    x = torch.randn(2, blk.conv2.in_channels, 12, 12)
+    for conv, bn in ((blk.conv2, blk.bn2), (blk.downsample[0], blk.downsample[1])):
+        xin = x if conv is blk.conv2 else torch.randn(2, conv.in_channels, 12, 12)
+        with torch.no_grad():
+            ref = bn(conv(xin))
+            w, b = phdfx.fold_conv_bn(conv, bn)
+            got = F.conv2d(xin, w, b, stride=conv.stride, padding=conv.padding)
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_plan_structure(plan):
+    kinds = [l.kind for l in plan.layers]
+    assert kinds[0] == 1 and kinds[1] == 2 and kinds.count(0) == 52  # stem, maxpool, 52 bottleneck convs
+    assert len(plan.layers) == 54 and plan.names[-1] == "layer4.2.conv3"
+    assert sum(l.gap for l in plan.layers) == 1 and plan.layers[-1].gap == 1
+    # 16 conv3 with residual, 4 downsample without relu
+    assert sum(1 for l in plan.layers if l.res_buf >= 0) == 16
+    assert sum(1 for n, l in zip(plan.names, plan.layers) if n.endswith("downsample") and l.relu == 0) == 4
+    # MAC count per frame: 4 087 136 256 including the stem
+    macs = 0
+    for l in plan.layers:
+        if l.kind == 2:
+            continue
+        ho = (l.hin + 2 * l.pad - l.r) // l.stride + 1
+        macs += ho * ho * l.cout * l.cin * l.r * l.s
+    assert macs == 4_087_136_256
+    # no layer writes a buffer it reads
+    for l in plan.layers:
+        assert l.out_buf != l.in_buf and (l.res_buf < 0 or l.res_buf != l.out_buf or l.gap)
+    # offsets are 128-byte aligned and inside the blobs
+    for l in plan.layers:
+        if l.kind != 2:
+            assert l.w_off % 64 == 0 and l.w_off < plan.weights.numel() and l.b_off + l.cout <= plan.bias.numel()
+
+
+def test_dataflow_is_consistent(plan):
+    """Every buffer a layer reads was last written with the shape it expects."""
+    shape = {0: (224, 3)}
+    for name, l in zip(plan.names, plan.layers):
+        h, c = shape[l.in_buf]
+        assert (h, c) == (l.hin, l.cin), name
+        ho = (l.hin + 2 * l.pad - l.r) // l.stride + 1
+        if l.res_buf >= 0:
+            assert shape[l.res_buf] == (ho, l.cout), name
+        shape[l.out_buf] = (ho, l.cout)
+
+
+def test_pack_conv_layout():
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)  # [Cout,Cin,R,S]
+    p = phdfx.pack_conv(w).to(torch.float32).reshape(2, 3, 3, 3)  # [Cout,R,S,Cin]
+    for co in range(2):
+        for r in range(3):
+            for s in range(3):
+                for ci in range(3):
+                    assert p[co, r, s, ci] == w[co, ci, r, s]
+
+
+def test_pack_stem_layout():
+    w = torch.randn(64, 3, 7, 7)
+    p = phdfx.pack_stem(w).to(torch.float32).reshape(7, 64, 8, 4)
+    assert torch.count_nonzero(p[:, :, 0]) == 0 and torch.count_nonzero(p[..., 3]) == 0
+    wb = w.to(torch.bfloat16).to(torch.float32)
+    for r in (0, 3, 6):
+        for s in (0, 2, 6):
+            assert torch.equal(p[r, :, s + 1, :3], wb[:, :, r, s])
+
+
+def test_packed_weights_reproduce_the_network(backbone, plan):
+    """Unpack layer2.0.conv2 from the blob and check it against the module (closes the loop pack -> offsets)."""
+    i = plan.names.index("layer2.0.conv2")
+    l = plan.layers[i]
+    k = l.r * l.s * l.cin
+    w = plan.weights[l.w_off:l.w_off + l.cout * k].to(torch.float32).reshape(l.cout, l.r, l.s, l.cin)
+    blk = backbone[5][0]
+    wf, bf = phdfx.fold_conv_bn(blk.conv2, blk.bn2)
+    assert torch.equal(w.permute(0, 3, 1, 2), wf.to(torch.bfloat16).to(torch.float32))
+    assert torch.equal(plan.bias[l.b_off:l.b_off + l.cout], bf)
+
+
+def test_randomize_bn_matches_oracle_builder(backbone):
+    import torchvision
+
+    torch.manual_seed(R.WEIGHT_SEED)
+    bb = torch.nn.Sequential(*list(torchvision.models.resnet50(weights=None).children())[:-1]).eval()
+    phdfx.randomize_bn_(bb, R.BN_SEED)
+    for (n1, p1), (n2, p2) in zip(bb.state_dict().items(), backbone.state_dict().items()):
+        assert n1 == n2 and torch.equal(p1, p2), n1
