@@ -19,8 +19,10 @@ namespace {
 thread_local std::string g_last_error;
 
 struct LayerMaps {
-  CUtensorMap a;  // A operand over the arena input buffer (max_frames extent)
+  CUtensorMap a;  // A operand (activations; max_frames extent for arena maps)
   CUtensorMap b;  // weights
+  CUtensorMap o;  // output tile store (unused for gap layers)
+  CUtensorMap r;  // residual tile load (unused when the layer has no residual)
   bool valid = false;
 };
 
@@ -162,10 +164,32 @@ int validate_layer(phdfx_t* h, const phdfx_layer_desc& L, int id) {
   return 0;
 }
 
-// Build the A-operand and weight tensor maps of a conv layer for input pointer `in` holding `frames` frames.
-int build_maps(phdfx_t* h, const phdfx_layer_desc& L, const void* in, int frames, LayerMaps* out) {
+// Build the tensor maps of a conv layer: A operand over `in`, weights, output store over `outp`, residual load over
+// `res` (nullable), all for `frames` frames.
+int build_maps(phdfx_t* h, const phdfx_layer_desc& L, const void* in, const void* res, void* outp, int frames,
+               LayerMaps* out) {
   const Geo g = geometry(L);
   const __nv_bfloat16* w = h->d_weights + L.w_off;
+  memset(&out->o, 0, sizeof(CUtensorMap));
+  memset(&out->r, 0, sizeof(CUtensorMap));
+  {
+    const cuuint64_t cout = L.cout;
+    const cuuint64_t rows = static_cast<cuuint64_t>(frames) * g.P * g.Q;
+    cuuint64_t od[2] = {cout, rows};
+    cuuint64_t os[1] = {cout * 2};
+    cuuint32_t ob[2] = {kGroupCols, kBlockM};
+    if (g.mode == MODE_STEM) {
+      cuuint64_t d4[4] = {64, kStemOut, kStemOut, static_cast<cuuint64_t>(frames)};
+      cuuint64_t s4[3] = {128, 128ull * kStemOut, 128ull * kStemOut * kStemOut};
+      cuuint32_t b4[4] = {64, kStemTileQ, kStemTileP, 1};
+      if (int rc = encode_tiled(h, &out->o, outp, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_128B, "stem out")) return rc;
+    } else if (g.mode != MODE_GAP) {
+      if (int rc = encode_tiled(h, &out->o, outp, 2, od, os, ob, CU_TENSOR_MAP_SWIZZLE_128B, "out")) return rc;
+    }
+    if (res != nullptr) {
+      if (int rc = encode_tiled(h, &out->r, res, 2, od, os, ob, CU_TENSOR_MAP_SWIZZLE_128B, "residual")) return rc;
+    }
+  }
   if (g.mode == MODE_STEM) {
     // dims: k (8 px * 4 ch window) | q (stride 2 px = 16 B) | row parity | p' = row/2 | frame
     const cuuint64_t row_b = static_cast<cuuint64_t>(kStemWPad) * 4 * 2;
@@ -228,14 +252,14 @@ int launch_conv_t(phdfx_t* h, const LayerMaps& maps, const ConvParams& p, cudaSt
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  conv_igemm_kernel<BN, MODE><<<grid, kNumThreads, Cfg::SMEM_BYTES, st>>>(maps.a, maps.b, p);
+  conv_igemm_kernel<BN, MODE><<<grid, kNumThreads, Cfg::SMEM_BYTES, st>>>(maps.a, maps.b, maps.o, maps.r, p);
   CUDA_TRY(h, cudaGetLastError());
   h->last_launches++;
   return 0;
 }
 
-int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, const void* residual, void* out,
-                int n, cudaStream_t st) {
+int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bool has_res, void* out, int n,
+                cudaStream_t st) {
   const Geo g = geometry(L);
   ConvParams p{};
   p.Cout = L.cout;
@@ -249,9 +273,8 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, co
   p.relu = L.relu;
   p.n_frames = n;
   p.bias = h->d_bias + L.b_off;
-  p.residual = static_cast<const __nv_bfloat16*>(residual);
-  p.out = static_cast<__nv_bfloat16*>(out);
-  p.feats = static_cast<float*>(out);
+  p.has_res = has_res ? 1 : 0;
+  p.feats = L.gap ? static_cast<float*>(out) : nullptr;
   p.M = n * g.P * g.Q;
   p.n_tiles = L.cout / g.bn;
   if (g.mode == MODE_STEM)
@@ -415,7 +438,11 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
     const auto& L = h->layers[i];
     if (L.kind == PHDFX_MAXPOOL) continue;
     if (!h->bufs[L.in_buf]) return fail(h, PHDFX_ERR_INVALID, "layer %d reads buffer %d that no layer writes", i, L.in_buf);
-    if (int rc = build_maps(h, L, h->bufs[L.in_buf], h->max_frames, &h->maps[i])) return rc;
+    if (L.res_buf >= 0 && !h->bufs[L.res_buf])
+      return fail(h, PHDFX_ERR_INVALID, "layer %d adds buffer %d that no layer writes", i, L.res_buf);
+    if (int rc = build_maps(h, L, h->bufs[L.in_buf], L.res_buf >= 0 ? h->bufs[L.res_buf] : nullptr,
+                            L.gap ? nullptr : h->bufs[L.out_buf], h->max_frames, &h->maps[i]))
+      return rc;
   }
   CUDA_TRY(h, cudaDeviceSynchronize());
   return 0;
@@ -463,11 +490,14 @@ static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cud
       continue;
     }
     if (L.in_buf == 0 && d_in != nullptr && d_in != h->bufs[0]) {
+      // external input buffer: it holds only n frames, so its A map is built per call; the output map over the
+      // arena (max_frames extent) is reused
       LayerMaps tmp;
-      if (int rc = build_maps(h, L, d_in, n, &tmp)) return rc;
-      if (int rc = launch_conv(h, L, tmp, res, out, n, st)) return rc;
+      if (int rc = build_maps(h, L, d_in, res, L.gap ? nullptr : out, n, &tmp)) return rc;
+      tmp.o = h->maps[i].o;
+      if (int rc = launch_conv(h, L, tmp, res != nullptr, out, n, st)) return rc;
     } else {
-      if (int rc = launch_conv(h, L, h->maps[i], res, out, n, st)) return rc;
+      if (int rc = launch_conv(h, L, h->maps[i], res != nullptr, out, n, st)) return rc;
     }
     if (L.gap) wrote_feats = true;
   }
@@ -501,8 +531,9 @@ int phdfx_run_layer(phdfx_t* h, int layer_id, const void* d_in, const void* d_re
   if (L.kind == PHDFX_MAXPOOL) return launch_maxpool(h, L, d_in, d_out, n, st);
   if (L.res_buf >= 0 && !d_residual) return fail(h, PHDFX_ERR_INVALID, "layer %d needs a residual input", layer_id);
   LayerMaps tmp;
-  if (int rc = build_maps(h, L, d_in, n, &tmp)) return rc;
-  return launch_conv(h, L, tmp, L.res_buf >= 0 ? d_residual : nullptr, d_out, n, st);
+  const void* res = L.res_buf >= 0 ? d_residual : nullptr;
+  if (int rc = build_maps(h, L, d_in, res, L.gap ? nullptr : d_out, n, &tmp)) return rc;
+  return launch_conv(h, L, tmp, res != nullptr, d_out, n, st);
 }
 
 int phdfx_layer_count(const phdfx_t* h) { return h ? static_cast<int>(h->layers.size()) : 0; }

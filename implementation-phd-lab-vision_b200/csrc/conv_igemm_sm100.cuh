@@ -7,12 +7,17 @@
 // src/preprocess_resnet_features.py:296 `backbone(x)`).  BN is folded into W and a per-channel fp32 bias
 // on the host, so the epilogue is  y = relu?(acc + bias [+ residual]).
 //
-// Structure: one persistent CTA per SM, 6 warps, warp-specialised.
+// Structure: one persistent CTA per SM, 7 warps, warp-specialised.
 //   warp 0   TMA producer   A tile via tiled / im2col / stem-window tensor maps, W tile via a 2-D map, both
 //                           K-major with hardware swizzle, NSTAGE-deep mbarrier ring
 //   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM
 //                           accumulator; tcgen05.commit releases smem slots / publishes the accumulator
-//   warp 2-5 epilogue       tcgen05.ld -> bias/residual/ReLU -> bf16 -> global (or fused global-avg-pool)
+//   warp 2-5 epilogue       per 64-channel group: tcgen05.ld -> + bias (+ residual read from smem) -> ReLU -> bf16,
+//                           written IN PLACE into a 128x128B swizzled staging buffer (conflict-free 16 B accesses)
+//   warp 6   epilogue DMA   one thread: TMA-loads the residual tile into the staging buffer ahead of the epilogue
+//                           warps and TMA-stores the finished buffer; NB buffers, look-ahead kLook groups.
+// All global traffic of the kernel is therefore TMA (full 128 B lines); the only exception is the fused
+// global-average-pool mode, which writes 8 KB of fp32 features per frame directly.
 #pragma once
 #include "ptx_sm100.cuh"
 
@@ -26,7 +31,7 @@ enum ConvMode : int {
 };
 
 struct ConvParams {
-  int M;           // valid GEMM rows in this launch (pixels; frames*98/2... see mode)
+  int M;           // valid GEMM rows in this launch (output pixels)
   int Cout;        // GEMM N
   int num_kb;      // K blocks per tile
   int kb_per_tap;  // Cin / 64 (im2col)
@@ -35,18 +40,19 @@ struct ConvParams {
   int stride, pad;
   int m_tiles, n_tiles;
   int relu;
+  int has_res;     // residual tile is TMA-loaded through mapR
   int n_frames;
-  const float* bias;               // [Cout] folded BN bias
-  const __nv_bfloat16* residual;   // nullable, same layout as out
-  __nv_bfloat16* out;              // [M, Cout] NHWC activations
-  float* feats;                    // MODE_GAP: [n_frames, Cout]
+  const float* bias;  // [Cout] folded BN bias
+  float* feats;       // MODE_GAP: [n_frames, Cout]
 };
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 224;
 constexpr int kGapRowsPerFrame = 49;
 constexpr int kGapRows = 98;
 constexpr int kStemTileQ = 16, kStemTileP = 8, kStemOut = 112, kStemTilesPerFrame = (112 / 16) * (112 / 8);
+constexpr int kGroupCols = 64;                        // channels per epilogue group (= one 128 B swizzle row)
+constexpr int kStageOutBytes = kBlockM * 128;         // one staging buffer: 128 rows x 128 B
 
 template <int BN, int MODE>
 struct ConvCfg {
@@ -56,32 +62,43 @@ struct ConvCfg {
   static constexpr int B_BYTES = BN * ROWB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int A_TX = ((MODE == MODE_GAP) ? kGapRows : kBlockM) * ROWB;
+  static constexpr int NB = (MODE == MODE_GAP) ? 2 : 4;        // epilogue staging buffers
+  static constexpr int LOOK = (NB == 2) ? 1 : 2;               // residual loads run LOOK groups ahead of the stores
+  static constexpr int GROUPS = BN / kGroupCols;
   static constexpr int SCRATCH_BYTES = (MODE == MODE_GAP) ? kBlockM * 33 * 4 : 0;
-  static constexpr int TAIL_BYTES = 2048 + 2 * BN * 4 + SCRATCH_BYTES;  // barriers + bias double buffer + scratch
-  static constexpr int SMEM_BUDGET = 200 * 1024;
-  static constexpr int NSTAGE_RAW = (SMEM_BUDGET - TAIL_BYTES - 1024) / STAGE_BYTES;
+  static constexpr int TAIL_BYTES = 1024 + 2 * BN * 4 + SCRATCH_BYTES;  // barriers + bias double buffer + scratch
+  static constexpr int SMEM_MAX = 232448;                              // 227 KB
+  static constexpr int NSTAGE_RAW = (SMEM_MAX - 1024 - TAIL_BYTES - NB * kStageOutBytes) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + TAIL_BYTES + 1024;  // +1024: manual alignment slack
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;                // power of two for BN in {64,128,256}
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + NB * kStageOutBytes + TAIL_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
 };
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapR,
                   const ConvParams p) {
   using Cfg = ConvCfg<BN, MODE>;
   constexpr int NSTAGE = Cfg::NSTAGE;
+  constexpr int NB = Cfg::NB;
+  constexpr int LOOK = Cfg::LOOK;
+  constexpr int GROUPS = Cfg::GROUPS;
   static_assert(NSTAGE >= 2, "pipeline needs at least two stages");
+  static_assert(Cfg::SMEM_BYTES <= Cfg::SMEM_MAX, "shared memory budget exceeded");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tail = smem + NSTAGE * Cfg::STAGE_BYTES;
+  uint8_t* stage_out = smem + NSTAGE * Cfg::STAGE_BYTES;  // [NB][128][128 B], 1024-aligned
+  uint8_t* tail = stage_out + NB * kStageOutBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);  // [NSTAGE]
   uint64_t* empty_bar = full_bar + NSTAGE;                 // [NSTAGE]
   uint64_t* tmem_full = empty_bar + NSTAGE;                // [2]
   uint64_t* tmem_empty = tmem_full + 2;                    // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(tail + 2048);   // [2][BN]
+  uint64_t* res_full = tmem_empty + 2;                     // [NB] staging buffer holds the residual / is free
+  uint64_t* out_full = res_full + NB;                      // [NB] epilogue warps are done with the buffer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_full + NB);
+  float* s_bias = reinterpret_cast<float*>(tail + 1024);   // [2][BN]
   float* s_scratch = s_bias + 2 * BN;                      // MODE_GAP: [128][33]
 
   const int warp = threadIdx.x >> 5;
@@ -92,6 +109,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
   }
+  if (warp == 6 && lane == 0) {
+    if (MODE != MODE_GAP) tma_prefetch_desc(&mapO);
+    if (p.has_res) tma_prefetch_desc(&mapR);
+  }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -100,6 +121,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(&res_full[i], 1);
+      mbar_init(&out_full[i], 4);
     }
     fence_mbar_init();
   }
@@ -204,6 +229,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
       }
     }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ epilogue DMA (one thread)
+    if (lane == 0) {
+      const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x))
+                               ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                     static_cast<int>(gridDim.x)
+                               : 0;
+      const int J = my_tiles * GROUPS;
+      for (int t = 0; t < J + LOOK; ++t) {
+        if (t < J) {
+          // A(t): make buffer t % NB available to the epilogue warps (with the residual tile in it, if any)
+          if (MODE != MODE_GAP && t >= NB) tma_store_wait_read<NB - LOOK - 1>();  // store t-NB has left smem
+          const int b = t % NB;
+          if (p.has_res) {
+            const int tile = blockIdx.x + (t / GROUPS) * gridDim.x;
+            const int g = t % GROUPS;
+            const int m_blk = tile / p.n_tiles;
+            const int n_blk = tile - m_blk * p.n_tiles;
+            const int row0 = m_blk * ((MODE == MODE_GAP) ? kGapRows : kBlockM);
+            mbar_arrive_expect_tx(&res_full[b], kStageOutBytes);
+            tma_load_2d(&mapR, &res_full[b], stage_out + b * kStageOutBytes, n_blk * BN + g * kGroupCols, row0);
+          } else {
+            mbar_arrive(&res_full[b]);
+          }
+        }
+        if (t >= LOOK) {
+          // B(u): the epilogue warps finished buffer u % NB -> store it
+          const int u = t - LOOK;
+          const int b = u % NB;
+          mbar_wait(&out_full[b], (u / NB) & 1);
+          if (MODE != MODE_GAP) {
+            const int tile = blockIdx.x + (u / GROUPS) * gridDim.x;
+            const int g = u % GROUPS;
+            const int m_blk = tile / p.n_tiles;
+            const int n_blk = tile - m_blk * p.n_tiles;
+            const uint8_t* src = stage_out + b * kStageOutBytes;
+            if (MODE == MODE_STEM) {
+              const int n = m_blk / kStemTilesPerFrame;
+              const int tt = m_blk - n * kStemTilesPerFrame;
+              const int p0 = (tt / (kStemOut / kStemTileQ)) * kStemTileP;
+              const int q0 = (tt % (kStemOut / kStemTileQ)) * kStemTileQ;
+              tma_store_4d(&mapO, src, 0, q0, p0, n);
+            } else {
+              tma_store_2d(&mapO, src, n_blk * BN + g * kGroupCols, m_blk * kBlockM);
+            }
+            tma_store_commit();
+          }
+        }
+      }
+      if (MODE != MODE_GAP) tma_store_wait_all<0>();
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
@@ -212,6 +288,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
+    int jg = 0;  // running group counter (matches the DMA thread's t / u)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.n_tiles;
       const int n_blk = tile - m_blk * p.n_tiles;
@@ -220,96 +297,86 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int i = et; i < BN; i += 128) sb[i] = __ldg(&p.bias[n_base + i]);
       named_barrier_sync(1, 128);
 
-      // output row addressing
-      bool row_ok;
-      size_t row_off;  // element offset of this thread's output row
-      if (MODE == MODE_STEM) {
-        const int n = m_blk / kStemTilesPerFrame;
-        const int t = m_blk - n * kStemTilesPerFrame;
-        const int pp = (t / (kStemOut / kStemTileQ)) * kStemTileP + (row >> 4);
-        const int qq = (t % (kStemOut / kStemTileQ)) * kStemTileQ + (row & 15);
-        row_ok = n < p.n_frames;
-        row_off = ((static_cast<size_t>(n) * kStemOut + pp) * kStemOut + qq) * p.Cout;
-      } else if (MODE == MODE_GAP) {
-        const int m = m_blk * kGapRows + row;
-        row_ok = (row < kGapRows) && (m < p.M);
-        row_off = static_cast<size_t>(m) * p.Cout;
-      } else {
-        const int m = m_blk * kBlockM + row;
-        row_ok = m < p.M;
-        row_off = static_cast<size_t>(m) * p.Cout;
-      }
+      bool row_ok = true;
+      if (MODE == MODE_GAP) row_ok = (row < kGapRows) && (m_blk * kGapRows + row < p.M);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
-        // residual (bf16) for these 32 channels, issued before waiting on the TMEM load
-        uint4 rv[4];
-        const bool has_res = (p.residual != nullptr) && row_ok;
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n_base + c * 32);
+      for (int g = 0; g < GROUPS; ++g, ++jg) {
+        const int b = jg % NB;
+        mbar_wait(&res_full[b], (jg / NB) & 1);
+        uint8_t* row_ptr = stage_out + b * kStageOutBytes + row * 128;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + g * kGroupCols + h * 32, v);
+          tmem_ld_wait();
+          const float4* sb4 = reinterpret_cast<const float4*>(sb + g * kGroupCols + h * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = __ldg(rp + j);
-        }
-        tmem_ld_wait();
-        float f[32];
-        const float4* sb4 = reinterpret_cast<const float4*>(sb + c * 32);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            // 16-byte chunk (8 channels) of this thread's row; 128B-swizzle: physical chunk = logical ^ (row & 7)
+            uint4* sp = reinterpret_cast<uint4*>(row_ptr + (((h * 4 + c4) ^ (row & 7)) << 4));
+            const float4 b0 = sb4[2 * c4], b1 = sb4[2 * c4 + 1];
+            float f[8];
+            f[0] = __uint_as_float(v[8 * c4 + 0]) + b0.x;
+            f[1] = __uint_as_float(v[8 * c4 + 1]) + b0.y;
+            f[2] = __uint_as_float(v[8 * c4 + 2]) + b0.z;
+            f[3] = __uint_as_float(v[8 * c4 + 3]) + b0.w;
+            f[4] = __uint_as_float(v[8 * c4 + 4]) + b1.x;
+            f[5] = __uint_as_float(v[8 * c4 + 5]) + b1.y;
+            f[6] = __uint_as_float(v[8 * c4 + 6]) + b1.z;
+            f[7] = __uint_as_float(v[8 * c4 + 7]) + b1.w;
+            if (p.has_res) {
+              const uint4 rv = *sp;
+              f[0] += bf16_lo(rv.x);
+              f[1] += bf16_hi(rv.x);
+              f[2] += bf16_lo(rv.y);
+              f[3] += bf16_hi(rv.y);
+              f[4] += bf16_lo(rv.z);
+              f[5] += bf16_hi(rv.z);
+              f[6] += bf16_lo(rv.w);
+              f[7] += bf16_hi(rv.w);
+            }
+            if (p.relu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = sb4[j];
-          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-        }
-        if (has_res) {
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+            if (MODE == MODE_GAP) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t w[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              f[8 * j + 2 * q + 0] += bf16_lo(w[q]);
-              f[8 * j + 2 * q + 1] += bf16_hi(w[q]);
+              for (int j = 0; j < 8; ++j) s_scratch[row * 33 + c4 * 8 + j] = row_ok ? f[j] : 0.0f;
+            } else {
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]);
+              o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]);
+              o.w = pack_bf16x2(f[6], f[7]);
+              *sp = o;
             }
           }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        }
-        if (MODE == MODE_GAP) {
-          // deterministic in-CTA mean over the 49 rows of each of the tile's two frames
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s_scratch[row * 33 + j] = row_ok ? f[j] : 0.0f;
-          named_barrier_sync(2, 128);
-          if (et < 64) {
-            const int fr = et >> 5;
-            const int col = et & 31;
-            const int frame = m_blk * 2 + fr;
-            float acc_sum = 0.0f;
-            for (int r = 0; r < kGapRowsPerFrame; ++r) acc_sum += s_scratch[(fr * kGapRowsPerFrame + r) * 33 + col];
-            if (frame < p.n_frames)
-              p.feats[static_cast<size_t>(frame) * p.Cout + n_base + c * 32 + col] =
-                  acc_sum * (1.0f / kGapRowsPerFrame);
-          }
-          named_barrier_sync(3, 128);
-        } else if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + row_off + n_base + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            op[j] = o;
+          if (MODE == MODE_GAP) {
+            // deterministic in-CTA mean over the 49 rows of each of the tile's two frames
+            named_barrier_sync(2, 128);
+            if (et < 64) {
+              const int fr = et >> 5;
+              const int col = et & 31;
+              const int frame = m_blk * 2 + fr;
+              float acc_sum = 0.0f;
+              for (int r = 0; r < kGapRowsPerFrame; ++r)
+                acc_sum += s_scratch[(fr * kGapRowsPerFrame + r) * 33 + col];
+              if (frame < p.n_frames)
+                p.feats[static_cast<size_t>(frame) * p.Cout + n_base + g * kGroupCols + h * 32 + col] =
+                    acc_sum * (1.0f / kGapRowsPerFrame);
+            }
+            named_barrier_sync(3, 128);
           }
         }
+        // hand the buffer to the DMA thread (generic-proxy writes -> async proxy)
+        if (MODE != MODE_GAP) fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_full[b]);
       }
       // release the accumulator buffer to the MMA warp
       tc_fence_before();
