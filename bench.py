@@ -53,28 +53,55 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clocks / throttle reasons sampled DURING the timed region through NVML (pynvml, ~1 kHz capable; the
+    nvidia-smi CLI takes longer per query than a whole timed region lasts).  Falls back to nvidia-smi."""
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.samples = []  # (sm_mhz, reasons_bitmask)
+        self.sm_max = None
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self._nvml = None
 
     def _run(self):
+        nv = self._nvml
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if nv is not None:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                    try:
+                        reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                    except Exception:  # noqa: BLE001
+                        reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    self.samples.append((mhz, reasons))
+                    self._stop.wait(0.004)
+                else:
+                    out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm",
+                                          "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append((float(out[0]), 0))
+                    self.sm_max = float(out[1])
+                    self._stop.wait(0.05)
             except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.15)
+                self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -86,20 +113,18 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = []
-        reasons = set()
-        smax = None
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                smax = float(r[1])
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        # NVML clocks-event-reason bits (nvml.h): 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal_slowdown,
+        # 0x40 hw_thermal_slowdown, 0x80 hw_power_brake_slowdown
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown"}
+        sm = [s[0] for s in self.samples]
+        mask = 0
+        for s in self.samples:
+            mask |= s[1]
+        reasons = sorted(n for b, n in names.items() if mask & b)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "sm_mhz_min": float(min(sm)) if sm else None,
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def reference_cpu_steps(steps: int, warmup: int, frames_per_step: int):

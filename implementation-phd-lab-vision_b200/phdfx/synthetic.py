@@ -1,0 +1,63 @@
+"""Synthetic H36M-shaped clips for benchmarks, tests and `--synthetic` runs of the entry point.
+
+Stands in for `Human36MPreprocessedClips` (src/dataset.py:210-437) when there is no dataset (the licensed H36M videos
+and the video decoder are outside this drop-in): same index fields (`subject, action, cam, start, end`,
+dataset.py:49-58) and the same per-clip outputs, except that frames stay uint8 and un-cropped, with the person box
+next to them — crop / resize / normalise move to the GPU (K1)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+
+@dataclass
+class ClipIndex:
+    subject: int
+    action: str
+    cam: str
+    start: int
+    end: int
+
+
+class SyntheticH36MClips(Dataset):
+    """len = n_clips; item = (frames uint8 (T,H,W,3), joints3d (T,17,3) mm, joints2d (T,17,2) px in the 224 crop,
+    K (3,3), box int64 (top,left,h,w)).  Everything is a pure function of (seed, clip index)."""
+
+    def __init__(self, n_clips: int, seq_len: int = 40, height: int = 224, width: int = 224,
+                 subjects: Tuple[int, ...] = (1, 6, 7, 8), seed: int = 0, box_side: int = 0):
+        self.n_clips, self.seq_len, self.h, self.w, self.seed = n_clips, seq_len, height, width, seed
+        side = box_side if box_side > 0 else min(height, width)
+        self.side = min(side, height, width)
+        self.index: List[ClipIndex] = []
+        for i in range(n_clips):
+            self.index.append(ClipIndex(subject=int(subjects[i % len(subjects)]), action=f"Action_{(i // 7) % 15}",
+                                        cam=f"cam_{i % 4}", start=5 * i, end=5 * i + seq_len))
+
+    def __len__(self):
+        return self.n_clips
+
+    def box(self, i: int) -> torch.Tensor:
+        rng = np.random.default_rng((self.seed, i, 1))
+        top = int(rng.integers(0, self.h - self.side + 1))
+        left = int(rng.integers(0, self.w - self.side + 1))
+        return torch.tensor([top, left, self.side, self.side], dtype=torch.int64)
+
+    def annotations(self, i: int):
+        rng = np.random.default_rng((self.seed, i, 2))
+        j3 = torch.from_numpy(rng.normal(0.0, 400.0, size=(self.seq_len, 17, 3)).astype(np.float32))
+        j3[..., 2] += 4000.0
+        j2 = torch.from_numpy(rng.uniform(0.0, 224.0, size=(self.seq_len, 17, 2)).astype(np.float32))
+        K = torch.tensor([[500.0, 0.0, 112.0], [0.0, 500.0, 112.0], [0.0, 0.0, 1.0]])
+        return j3, j2, K
+
+    def frames(self, i: int) -> torch.Tensor:
+        rng = np.random.default_rng((self.seed, i, 0))
+        return torch.from_numpy(rng.integers(0, 256, size=(self.seq_len, self.h, self.w, 3), dtype=np.uint8))
+
+    def __getitem__(self, i: int):
+        j3, j2, K = self.annotations(i)
+        return self.frames(i), j3, j2, K, self.box(i)

@@ -1,0 +1,334 @@
+"""Drop-in entry point: precompute per-clip ResNet-50 features for H36M on B200s.
+
+Same command line and the same on-disk output as the reference's script of the same name
+(/root/reference/src/preprocess_resnet_features.py:136-155 flags, :80-131,403-417 shard / index layout), so
+`dataset_features.py`, `samplers.py`, `model.py` and `train.py` run unchanged on what this writes.  What changes is
+the engine behind `backbone(x)` (:296): libphdfx.so (hand-written sm_100a kernels) instead of cuDNN / DataParallel /
+torch.compile, one process per GPU instead of nn.DataParallel (:214-217), pinned async copies instead of the blocking
+`.cpu()` (:297), and a write-once shard writer.
+
+    python -u src/preprocess_resnet_features.py --root ROOT --out OUT [--augment] ...           # real data (Seam A)
+    torchrun --nproc-per-node 8 src/preprocess_resnet_features.py --root ROOT --out OUT ...     # 8 GPUs
+    python -u src/preprocess_resnet_features.py --synthetic 64:224x224 --out OUT --weights random:0   # no dataset
+
+Real data needs the user's `dataset.py` (the reference's `Human36MPreprocessedClips`, which owns video decoding and
+annotation handling — outside this drop-in) importable, e.g. by running from the reference's src/ directory or with
+--dataset-path.  Extra flags: --backend {b200,torch}, --synthetic, --weights, --dataset-path, --max-clips.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+
+_ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(_ROOT / "implementation-phd-lab-vision_b200"))
+
+from phdfx.dist import gather_rows, shard_range  # noqa: E402
+from phdfx.shards import AUG_NAMES, ClipRecord, ShardWriter  # noqa: E402
+from phdfx.synthetic import SyntheticH36MClips  # noqa: E402
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser("B200-native: precompute per-clip ResNet50 features for H36M")
+    # --- the reference's 13 flags, same names and defaults (:137-153) ---
+    p.add_argument("--root", type=str, default=None, help="H36M preprocessed root")
+    p.add_argument("--out", type=str, required=True, help="Output directory for cached features")
+    p.add_argument("--seq-len", type=int, default=40)
+    p.add_argument("--frame-skip", type=int, default=2)
+    p.add_argument("--stride", type=int, default=5)
+    p.add_argument("--batch-size", type=int, default=32)
+    p.add_argument("--num-workers", type=int, default=8)
+    p.add_argument("--subjects", type=int, nargs="+", default=[1, 5, 6, 7, 8, 9, 11])
+    p.add_argument("--device", type=str, default="cuda")
+    p.add_argument("--save-fp16", action="store_true", help="Store feats as float16")
+    p.add_argument("--augment", action="store_true", help="4 variants per clip: orig, cjitter, hflip, trev")
+    p.add_argument("--shard-size", type=int, default=512, help="Number of clips per shard file")
+    p.add_argument("--shuffle-pool", type=int, default=8192)
+    p.add_argument("--shuffle-seed", type=int, default=123)
+    # --- additions ---
+    p.add_argument("--backend", choices=["b200", "torch"], default="b200",
+                   help="b200: libphdfx.so (no fallback); torch: the reference's eager path (for comparison runs)")
+    p.add_argument("--synthetic", type=str, default=None, metavar="N[:HxW[:SIDE]]",
+                   help="use N synthetic clips of HxW uint8 frames (person box side SIDE) instead of --root")
+    p.add_argument("--weights", type=str, default="imagenet",
+                   help="'imagenet' (torchvision IMAGENET1K_V2, needs network/cache), 'random:SEED', or a state_dict path")
+    p.add_argument("--dataset-path", type=str, default=None, help="directory holding the user's dataset.py")
+    p.add_argument("--max-clips", type=int, default=None)
+    p.add_argument("--jitter-seed", type=int, default=0, help="seed of the colour-jitter variant (synthetic mode)")
+    return p.parse_args(argv)
+
+
+def build_torch_backbone(weights: str) -> nn.Module:
+    """The reference's construction (:207-209)."""
+    from torchvision import models
+
+    if weights == "imagenet":
+        resnet = models.resnet50(weights=models.ResNet50_Weights.IMAGENET1K_V2)
+    elif weights.startswith("random:"):
+        torch.manual_seed(int(weights.split(":", 1)[1]))
+        resnet = models.resnet50(weights=None)
+    else:
+        resnet = models.resnet50(weights=None)
+        sd = torch.load(weights, map_location="cpu", weights_only=True)
+        resnet.load_state_dict(sd.get("state_dict", sd))
+    return nn.Sequential(*list(resnet.children())[:-1]).eval()
+
+
+def dist_setup():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return world, rank, local
+
+
+def real_dataset(args):
+    if args.dataset_path:
+        sys.path.insert(0, args.dataset_path)
+    try:
+        from dataset import Human36MPreprocessedClips  # the user's / reference's dataset.py
+    except Exception as e:  # noqa: BLE001
+        raise RuntimeError(
+            "real-data mode needs the reference's dataset.py importable (run from its src/ directory or pass "
+            f"--dataset-path); import failed with: {e!r}.  Use --synthetic N to run without a dataset.") from e
+    return Human36MPreprocessedClips(root=args.root, subjects=args.subjects, seq_len=args.seq_len,
+                                     frame_skip=args.frame_skip, stride=args.stride, augment=args.augment,
+                                     max_clips=args.max_clips)
+
+
+def parse_synthetic(spec: str, args):
+    parts = spec.split(":")
+    n = int(parts[0])
+    h = w = 224
+    side = 0
+    if len(parts) > 1:
+        h, w = (int(v) for v in parts[1].lower().split("x"))
+    if len(parts) > 2:
+        side = int(parts[2])
+    if args.max_clips is not None:
+        n = min(n, args.max_clips)
+    return SyntheticH36MClips(n, seq_len=args.seq_len, height=h, width=w, subjects=tuple(args.subjects), seed=0,
+                              box_side=side)
+
+
+@torch.no_grad()
+def main(argv=None):
+    args = parse_args(argv)
+    world, rank, local = dist_setup()
+    is_main = rank == 0
+    log = print if is_main else (lambda *a, **k: None)
+
+    if args.backend == "b200":
+        if not torch.cuda.is_available():
+            raise RuntimeError("--backend b200 needs a CUDA sm_100 device; there is no CPU fallback "
+                               "(use --backend torch for the reference's eager path)")
+        device = torch.device("cuda", local)
+    else:
+        # the reference's behaviour (:157-161): fall back to CPU when CUDA is missing
+        device = torch.device("cuda", local) if (args.device.startswith("cuda") and torch.cuda.is_available()) \
+            else torch.device("cpu")
+    n_vars = len(AUG_NAMES) if args.augment else 1
+    T = args.seq_len
+    out_root = Path(args.out)
+    if is_main:
+        out_root.mkdir(parents=True, exist_ok=True)
+    log(f"Device     : {device}  (world size {world}, backend {args.backend})")
+    log(f"Augment    : {args.augment}  ({'4 variants/clip -> ' + ', '.join(AUG_NAMES) if args.augment else 'none'})")
+    log(f"Shard size : {args.shard_size} clips  ({args.shard_size * n_vars} variant entries/shard)")
+
+    synthetic = args.synthetic is not None
+    if not synthetic and not args.root:
+        raise SystemExit("either --root or --synthetic is required")
+    ds = parse_synthetic(args.synthetic, args) if synthetic else real_dataset(args)
+    n_clips = len(ds)
+
+    torch_backbone = build_torch_backbone(args.weights)
+    if args.backend == "b200":
+        import phdfx
+
+        frames_per_call = args.batch_size * T
+        backbone = phdfx.B200Backbone(torch_backbone, device=device, max_frames=min(frames_per_call, 1280))
+    else:
+        backbone = torch_backbone.to(device)
+    feat_dtype = torch.float16 if args.save_fp16 else torch.float32
+
+    def run_normalised(v_video: torch.Tensor) -> torch.Tensor:
+        """(Bv,T,3,224,224) fp32 normalised -> (Bv,T,2048) on the device — the reference's lines :288-296."""
+        v_video = v_video.to(device, non_blocking=True)
+        Bv, Tt, C, H, W = v_video.shape
+        x = v_video.view(Bv * Tt, C, H, W).contiguous()
+        if args.backend == "torch":
+            with torch.autocast(device_type=device.type, dtype=torch.bfloat16, enabled=device.type == "cuda"):
+                return backbone(x).flatten(1).view(Bv, Tt, -1).float()
+        return backbone(x).flatten(1).view(Bv, Tt, -1)
+
+    def run_u8(frames: torch.Tensor, boxes: torch.Tensor, flip: bool) -> torch.Tensor:
+        """Seam B: (Bv,T,H,W,3) uint8 + per-clip boxes -> (Bv,T,2048) on the device."""
+        Bv, Tt, H, W, _ = frames.shape
+        if args.backend == "torch":
+            # the reference's own front end (src/dataset.py:141-152, :166, :242-245), clip by clip
+            import torchvision.transforms.functional as TF
+
+            mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
+            std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+            vids = []
+            for b in range(Bv):
+                top, left, hh, ww = (int(v) for v in boxes[b])
+                v = frames[b].permute(0, 3, 1, 2)[:, :, top:top + hh, left:left + ww]
+                v = TF.resize(v, [224, 224], antialias=False).to(torch.float32) / 255.0
+                if flip:
+                    v = torch.flip(v, dims=[-1])
+                vids.append((v - mean) / std)
+            return run_normalised(torch.stack(vids))
+        fr = frames.view(Bv * Tt, H, W, 3).to(device, non_blocking=True)
+        bx = boxes.to(torch.int32).repeat_interleave(Tt, dim=0).to(device, non_blocking=True)
+        return backbone.extract_u8(fr, bx, flip_w=flip).view(Bv, Tt, -1)
+
+    def jitter_variant(frames: torch.Tensor, boxes: torch.Tensor, clip_ids) -> torch.Tensor:
+        """Colour-jitter variant in synthetic mode: the reference's recipe (src/dataset.py:188-198: ColorJitter on
+        the resized [0,1] clip, then Normalize) evaluated on the device, one jitter draw per clip."""
+        import torch.nn.functional as F
+        from torchvision.transforms import v2 as T2
+
+        jit = T2.ColorJitter(brightness=0.3, contrast=0.3, saturation=0.2, hue=0.05)
+        mean = torch.tensor(IMAGENET_MEAN, device=device).view(1, 3, 1, 1)
+        std = torch.tensor(IMAGENET_STD, device=device).view(1, 3, 1, 1)
+        outs = []
+        for b in range(frames.shape[0]):
+            top, left, hh, ww = (int(v) for v in boxes[b])
+            crop = frames[b, :, top:top + hh, left:left + ww].to(device).permute(0, 3, 1, 2).float()
+            if (hh, ww) != (224, 224):
+                crop = F.interpolate(crop, size=(224, 224), mode="bilinear", align_corners=False).round()
+            torch.manual_seed(args.jitter_seed * 1_000_003 + int(clip_ids[b]))
+            vid = jit(crop / 255.0)
+            outs.append((vid - mean) / std)
+        return run_normalised(torch.stack(outs))
+
+    writer = ShardWriter(out_root, n_vars, args.shard_size, args.shuffle_pool, args.shuffle_seed) if is_main else None
+
+    # clips are dealt out in global batches of (world * batch_size): rank r takes the r-th contiguous slice, so
+    # rank 0 can append clips to the shuffle pool in the reference's order after every gather
+    B = args.batch_size
+    t_all = time.time()
+    t_last = t_all
+    done = 0
+    for g0 in range(0, n_clips, B * world):
+        g1 = min(n_clips, g0 + B * world)
+        lo, hi = shard_range(g1 - g0, rank, world)
+        ids = list(range(g0 + lo, g0 + hi))
+        feats = torch.empty(0, n_vars, T, 2048, device=device)
+        small = []  # per clip: (joints3d[v], joints2d[v], K[v], box)
+        if ids:
+            items = [ds[i] for i in ids] if synthetic or args.num_workers == 0 else _loader_fetch(ds, ids, args)
+            if synthetic:
+                frames = torch.stack([it[0] for it in items])
+                boxes = torch.stack([it[4] for it in items])
+                f_orig = run_u8(frames, boxes, False)
+                if args.augment:
+                    f_jit = jitter_variant(frames, boxes, ids)
+                    f_flip = run_u8(frames, boxes, True)
+                    f_trev = torch.flip(f_orig, dims=[1])  # frames are independent: exact
+                    feats = torch.stack([f_orig, f_jit, f_flip, f_trev], dim=1)
+                else:
+                    feats = f_orig.unsqueeze(1)
+                for it in items:
+                    j3, j2, K, box = it[1], it[2], it[3], it[4]
+                    if args.augment:
+                        small.append(_augment_annotations(j3, j2, K))
+                    else:
+                        small.append(([j3], [j2], [K], box))
+            else:
+                if args.augment:  # item = list of 4 (video, j3d, j2d, K) variants (src/dataset.py:411-426)
+                    vids = [torch.stack([it[v][0] for it in items]) for v in range(n_vars)]
+                    f = [run_normalised(vids[0]), run_normalised(vids[1]), run_normalised(vids[2])]
+                    f.append(torch.flip(f[0], dims=[1]))  # trev == reversed orig (dataset.py:201-207)
+                    feats = torch.stack(f, dim=1)
+                    for it in items:
+                        small.append(([it[v][1] for v in range(4)], [it[v][2] for v in range(4)],
+                                      [it[v][3] for v in range(4)], None))
+                else:
+                    feats = run_normalised(torch.stack([it[0] for it in items])).unsqueeze(1)
+                    for it in items:
+                        small.append(([it[1]], [it[2]], [it[3]], it[4]))
+        feats = feats.to(feat_dtype)
+        all_feats = gather_rows(feats.contiguous(), g1 - g0, dst=0)
+        if world > 1:
+            import torch.distributed as dist
+
+            gathered = [None] * world if is_main else None
+            dist.gather_object(small, gathered, dst=0)
+            small_all = [s for part in gathered for s in part] if is_main else None
+        else:
+            small_all = small
+        if is_main:
+            host = all_feats.cpu()
+            for k in range(g1 - g0):
+                clip = ds.index[g0 + k]
+                j3s, j2s, Ks, box = small_all[k]
+                metas = [{"subject": clip.subject, "action": clip.action, "cam": clip.cam, "start": clip.start,
+                          "end": clip.end, "aug": AUG_NAMES[v] if args.augment else "orig",
+                          "box": box if not args.augment else None} for v in range(n_vars)]
+                writer.add(ClipRecord([host[k, v] for v in range(n_vars)], j3s, j2s, Ks, metas))
+            done = g1
+            if done % 200 < B * world or done == n_clips:
+                dt = time.time() - t_last
+                t_last = time.time()
+                log(f"[{100 * done / n_clips:5.1f}%] {done:6d}/{n_clips} clips | shard {writer.shard_id} "
+                    f"(pool: {len(writer.pool)} clips, carry: {len(writer.carry)} clips) | {dt:5.2f}s")
+    if is_main:
+        log("\nWaiting for all shards to be written to disk...")
+        writer.finish(seq_len=args.seq_len, frame_skip=args.frame_skip, save_fp16=args.save_fp16,
+                      augment=args.augment)
+        total = time.time() - t_all
+        log("-" * 60)
+        log(f"Done: {n_clips} clips x {n_vars} variant(s) packed into {writer.shard_id} shard(s)")
+        log(f"Total time {total:.1f}s | {n_clips / max(total, 1e-9):.1f} clips/s "
+            f"({n_clips * n_vars * T / max(total, 1e-9):.0f} frames/s)")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _augment_annotations(j3, j2, K):
+    """Annotation side of the four variants (src/dataset.py:158-207): hflip mirrors x and swaps left/right joints."""
+    flip_pairs = [(1, 4), (2, 5), (3, 6), (14, 11), (15, 12), (16, 13)]  # src/dataset.py:39-46
+    j2f, j3f, Kf = j2.clone(), j3.clone(), K.clone()
+    j2f[..., 0] = 224 - j2f[..., 0]
+    j3f[..., 0] = -j3f[..., 0]
+    for l, r in flip_pairs:
+        j2f[:, [l, r]] = j2f[:, [r, l]]
+        j3f[:, [l, r]] = j3f[:, [r, l]]
+    Kf[0, 2] = 224 - Kf[0, 2]
+    return ([j3, j3, j3f, torch.flip(j3, dims=[0])], [j2, j2, j2f, torch.flip(j2, dims=[0])], [K, K, Kf, K], None)
+
+
+def _loader_fetch(ds, ids, args):
+    """Decode a list of clips with DataLoader workers (the reference's :195-204 worker pool, per global batch)."""
+    from torch.utils.data import DataLoader, Subset
+
+    loader = DataLoader(Subset(ds, ids), batch_size=1, shuffle=False, num_workers=min(args.num_workers, len(ids)),
+                        collate_fn=lambda b: b[0])
+    return list(loader)
+
+
+if __name__ == "__main__":
+    main()

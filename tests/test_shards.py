@@ -1,0 +1,167 @@
+"""On-disk contract: what phdfx.shards writes is what the reference's reader consumes, and — given
+the same clips — exactly what the reference's own writer functions produce."""
+import os
+import random
+import sys
+
+import pytest
+import torch
+
+from conftest import REFERENCE_SRC
+from phdfx.shards import AUG_NAMES, AsyncShardWriter, ClipRecord, ShardWriter
+
+HAVE_REF = os.path.isdir(REFERENCE_SRC)
+
+
+def make_records(n_clips, n_vars, T=6, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    recs = []
+    for i in range(n_clips):
+        feats = [torch.randn(T, 2048, generator=g) for _ in range(n_vars)]
+        j3 = [torch.randn(T, 17, 3, generator=g) * 1000 for _ in range(n_vars)]
+        j2 = [torch.rand(T, 17, 2, generator=g) * 224 for _ in range(n_vars)]
+        K = [torch.eye(3) * (i + 1) for _ in range(n_vars)]
+        metas = [{"subject": [1, 6, 7, 8][i % 4], "action": f"Walk_{i % 3}", "cam": f"cam_{i % 4}", "start": 5 * i,
+                  "end": 5 * i + T, "aug": AUG_NAMES[v] if n_vars > 1 else "orig",
+                  "box": None if n_vars > 1 else torch.tensor([1, 2, 200, 200])} for v in range(n_vars)]
+        recs.append(ClipRecord(feats, j3, j2, K, metas))
+    return recs
+
+
+def write(tmp, recs, n_vars, shard_size, pool, seed=123, fp16=False):
+    w = ShardWriter(tmp, n_vars, shard_size=shard_size, shuffle_pool=pool, shuffle_seed=seed)
+    for r in recs:
+        w.add(r)
+    return w.finish(seq_len=6, frame_skip=2, save_fp16=fp16, augment=n_vars > 1)
+
+
+@pytest.mark.parametrize("n_vars", [1, 4])
+def test_layout_and_index(tmp_path, n_vars):
+    recs = make_records(23, n_vars)
+    index = write(tmp_path, recs, n_vars, shard_size=5, pool=8)
+    assert index["n_clips"] == 23 and index["n_shards"] == 5 and index["n_variants"] == n_vars
+    assert index["aug_names"] == (AUG_NAMES if n_vars == 4 else ["orig"]) and index["variants_grouped"] is True
+    assert sorted(os.listdir(tmp_path)) == ["index.pt"] + [f"shard_{i:05d}.pt" for i in range(5)]
+    # legacy (non-zip) pickle, loadable with weights_only=True like the reference reader (dataset_features.py:107)
+    with open(tmp_path / "shard_00000.pt", "rb") as f:
+        assert f.read(2) != b"PK"
+    idx = torch.load(tmp_path / "index.pt", map_location="cpu", weights_only=True)
+    seen = set()
+    for c in idx["clips"]:
+        shard = torch.load(tmp_path / f"shard_{c['shard_id']:05d}.pt", map_location="cpu", weights_only=True)
+        assert shard["n_vars"] == n_vars and shard["feats"].shape[1:] == (6, 2048)
+        assert shard["feats"].shape[0] == shard["joints3d"].shape[0] == len(shard["meta"])
+        assert c["row"] % n_vars == 0
+        m = shard["meta"][c["row"]]
+        assert (m["subject"], m["action"], m["cam"], m["start"]) == (c["subject"], c["action"], c["cam"], c["start"])
+        # find the source record and compare every variant row
+        src = next(r for r in recs if r.metas[0]["start"] == c["start"])
+        for v in range(n_vars):
+            assert torch.equal(shard["feats"][c["row"] + v], src.feats[v])
+            assert torch.equal(shard["K"][c["row"] + v], src.K[v])
+            assert shard["meta"][c["row"] + v]["aug"] == (AUG_NAMES[v] if n_vars > 1 else "orig")
+        seen.add(c["start"])
+    assert len(seen) == 23
+    sizes = [torch.load(tmp_path / f"shard_{i:05d}.pt", weights_only=True)["feats"].shape[0] // n_vars
+             for i in range(5)]
+    assert sizes == [5, 5, 5, 5, 3]  # full shards + one partial (:374-396)
+
+
+def test_empty_and_exact_multiple(tmp_path):
+    idx = write(tmp_path / "a", [], 1, shard_size=4, pool=8)
+    assert idx["n_shards"] == 0 and idx["clips"] == []
+    idx = write(tmp_path / "b", make_records(8, 1), 1, shard_size=4, pool=100)
+    assert idx["n_shards"] == 2
+
+
+def test_writer_errors_surface(tmp_path):
+    w = AsyncShardWriter()
+    w.save({"x": torch.zeros(1)}, tmp_path / "no_such_dir" / "f.pt")
+    with pytest.raises(RuntimeError):
+        w.wait()
+
+
+def test_variant_count_is_checked(tmp_path):
+    w = ShardWriter(tmp_path, 4)
+    with pytest.raises(ValueError):
+        w.add(make_records(1, 1)[0])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources only exist in the build container")
+@pytest.mark.parametrize("n_vars", [1, 4])
+def test_identical_to_reference_writer(tmp_path, n_vars):
+    """Feed the same clips through the REFERENCE's writer functions (imported unmodified) and through ours."""
+    import torchvision.io as tio
+
+    if not hasattr(tio, "VideoReader"):
+        tio.VideoReader = None  # shim: symbol removed upstream; not used by the functions called here
+    sys.path.insert(0, REFERENCE_SRC)
+    import preprocess_resnet_features as ref
+
+    recs = make_records(37, n_vars, seed=3)
+    shard_size, pool, seed = 4, 10, 123
+    # --- reference flow (:266-396), driven exactly like its main loop
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
+    writer = ref.AsyncFileWriter()
+    rng = random.Random(seed)
+    shuffle_pool, carry, clip_index, shard_id = [], [], [], 0
+    for r in recs:
+        shuffle_pool.append([{"feat": r.feats[v], "joints3d": r.joints3d[v], "joints2d": r.joints2d[v], "K": r.K[v],
+                              "meta": r.metas[v]} for v in range(n_vars)])
+        if len(shuffle_pool) >= pool:
+            shard_id, carry = ref.flush_pool_groups_to_shards(shuffle_pool, carry, shard_id, n_vars, ref_dir, writer,
+                                                              shard_size, clip_index, rng)
+            shuffle_pool = []
+    final = carry + shuffle_pool
+    rng.shuffle(final)
+    for s in range(0, len(final), shard_size):  # full shards then the partial one (:347-396)
+        groups = final[s:s + shard_size]
+        buf = ref.empty_shard_buffer()
+        for i, g in enumerate(groups):
+            m0 = g[0]["meta"]
+            clip_index.append({"shard_id": shard_id, "row": i * n_vars, "subject": m0["subject"],
+                               "action": m0["action"], "cam": m0["cam"], "start": m0["start"], "end": m0["end"]})
+            for e in g:
+                for k_src, k_dst in (("feat", "feats"), ("joints3d", "joints3d"), ("joints2d", "joints2d"), ("K", "K"),
+                                     ("meta", "meta")):
+                    buf[k_dst].append(e[k_src])
+        ref.flush_shard(buf, shard_id, n_vars, ref_dir, writer)
+        shard_id += 1
+    writer.wait()
+    writer.stop()
+    # --- ours
+    ours = write(tmp_path / "ours", recs, n_vars, shard_size, pool, seed)
+    assert ours["n_shards"] == shard_id and ours["clips"] == clip_index
+    for sid in range(shard_id):
+        a = torch.load(ref_dir / f"shard_{sid:05d}.pt", weights_only=True)
+        b = torch.load(tmp_path / "ours" / f"shard_{sid:05d}.pt", weights_only=True)
+        assert a.keys() == b.keys() and a["n_vars"] == b["n_vars"]
+        for k in ("feats", "joints3d", "joints2d", "K"):
+            assert torch.equal(a[k], b[k]) and a[k].dtype == b[k].dtype, (sid, k)
+        for ma, mb in zip(a["meta"], b["meta"]):
+            assert {k: v for k, v in ma.items() if k != "box"} == {k: v for k, v in mb.items() if k != "box"}
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources only exist in the build container")
+def test_reference_reader_and_sampler_consume_our_output(tmp_path):
+    """Unmodified Human36MFeatureClips + MixedShardBatchSampler over shards written by phdfx.shards."""
+    sys.path.insert(0, REFERENCE_SRC)
+    from dataset_features import Human36MFeatureClips
+    from samplers import MixedShardBatchSampler
+
+    recs = make_records(32, 4, seed=5)
+    write(tmp_path, recs, 4, shard_size=8, pool=16)
+    ds = Human36MFeatureClips(root=str(tmp_path), subjects=[1, 6, 7, 8], augment=True, shard_cache_size=8)
+    assert len(ds) == 32 * 4
+    feats, j3, j2, K = ds[5]
+    assert feats.shape == (6, 2048) and j3.shape == (6, 17, 3) and K.shape == (3, 3)
+    # row + var_offset addressing (dataset_features.py:116): item 5 = clip 1, variant 1
+    clip = ds._clips[1]
+    src = next(r for r in recs if r.metas[0]["start"] == clip["start"])
+    assert torch.equal(feats, src.feats[1]) and torch.allclose(j3, src.joints3d[1] / 1000.0)
+    sampler = MixedShardBatchSampler(ds, batch_size=8, shards_per_batch=4, shuffle=True, seed=0)
+    batches = list(sampler)
+    assert batches and all(len(b) == 8 for b in batches)
+    ds_test = Human36MFeatureClips(root=str(tmp_path), subjects=[6], test_set=True)
+    assert all(ds_test[i][4]["subject"] == 6 for i in range(len(ds_test)))
