@@ -1,0 +1,50 @@
+"""Small, deterministic launch sequences for ncu.
+
+    python tools/ncu_target.py step [batch]          # 2 warm-up steps + 1 step of the whole hot path (55 launches each)
+    python tools/ncu_target.py layers 0,3,5 [batch]  # each listed layer of the execution list twice via phdfx_run_layer
+"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200"))
+sys.path.insert(0, str(ROOT / "oracle"))
+
+import torch  # noqa: E402
+
+import phdfx  # noqa: E402
+import resnet50_ref as R  # noqa: E402
+
+
+def main():
+    mode = sys.argv[1]
+    if mode == "step":
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+        eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
+        frames = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            eng.extract_u8(frames, None)
+        torch.cuda.synchronize()
+        print("step done, launches per step:", eng.launches)
+    else:
+        ids = [int(v) for v in sys.argv[2].split(",")]
+        n = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+        eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
+        g = torch.Generator(device="cuda").manual_seed(0)
+        for i in ids:
+            L = eng.plan.layers[i]
+            if L.kind == 1:
+                x = torch.zeros(n, 224, 232, 4, device="cuda", dtype=torch.bfloat16)
+                x[:, :, 4:228, :3] = torch.randn(n, 224, 224, 3, device="cuda", generator=g).to(torch.bfloat16)
+            else:
+                x = torch.randn(n, L.hin, L.win, L.cin, device="cuda", generator=g).to(torch.bfloat16)
+            ho = (L.hin + 2 * L.pad - L.r) // L.stride + 1
+            res = torch.randn(n, ho, ho, L.cout, device="cuda", generator=g).to(torch.bfloat16) if L.res_buf >= 0 else None
+            for _ in range(2):
+                eng.run_layer(i, x, res)
+            torch.cuda.synchronize()
+            print("layer", i, eng.plan.names[i], "done")
+
+
+if __name__ == "__main__":
+    main()
