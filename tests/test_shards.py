@@ -95,8 +95,14 @@ def test_identical_to_reference_writer(tmp_path, n_vars):
 
     if not hasattr(tio, "VideoReader"):
         tio.VideoReader = None  # shim: symbol removed upstream; not used by the functions called here
-    sys.path.insert(0, REFERENCE_SRC)
-    import preprocess_resnet_features as ref
+    sys.path.insert(0, REFERENCE_SRC)  # for the reference script's own `from dataset import ...`
+    import importlib.util
+
+    # load by path under a private name: our drop-in script has the same file name as the reference's
+    spec = importlib.util.spec_from_file_location("reference_preprocess_resnet_features",
+                                                  os.path.join(REFERENCE_SRC, "preprocess_resnet_features.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
 
     recs = make_records(37, n_vars, seed=3)
     shard_size, pool, seed = 4, 10, 123
