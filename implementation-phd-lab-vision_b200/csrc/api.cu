@@ -5,12 +5,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "../../include/phdfx.h"
 #include "conv_igemm_sm100.cuh"
 #include "elementwise_sm100.cuh"
+#include "stem_pool_sm100.cuh"
 
 using namespace phdfxk;
 
@@ -131,6 +133,7 @@ Geo geometry(const phdfx_layer_desc& L) {
 }
 
 size_t out_elems_per_frame(const phdfx_layer_desc& L) {
+  if (L.kind == PHDFX_STEM_POOL) return static_cast<size_t>(kSpPool) * kSpPool * 64;
   if (L.kind == PHDFX_MAXPOOL) {
     const int Ho = (L.hin + 2 - 3) / 2 + 1, Wo = (L.win + 2 - 3) / 2 + 1;
     return static_cast<size_t>(Ho) * Wo * L.cout;
@@ -140,7 +143,7 @@ size_t out_elems_per_frame(const phdfx_layer_desc& L) {
 }
 
 int validate_layer(phdfx_t* h, const phdfx_layer_desc& L, int id) {
-  if (L.kind == PHDFX_STEM) {
+  if (L.kind == PHDFX_STEM || L.kind == PHDFX_STEM_POOL) {
     if (L.cin != 3 || L.cout != 64 || L.r != 7 || L.s != 7 || L.stride != 2 || L.pad != 3 || L.hin != kImg ||
         L.win != kImg)
       return fail(h, PHDFX_ERR_INVALID, "layer %d: stem must be 7x7/2 pad 3, 3->64, 224x224 input", id);
@@ -300,6 +303,35 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bo
   }
 }
 
+// Fused stem + max-pool (stem_pool_sm100.cuh).  `out` receives [n][56][56][64] bf16.
+int build_stem_pool_map(phdfx_t* h, void* out, int frames, CUtensorMap* m) {
+  cuuint64_t d[2] = {64, static_cast<cuuint64_t>(frames) * kSpPool * kSpPool};
+  cuuint64_t s[1] = {128};
+  cuuint32_t b[2] = {64, kSpPool};
+  return encode_tiled(h, m, out, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B, "stem+pool out");
+}
+
+int launch_stem_pool(phdfx_t* h, const phdfx_layer_desc& L, const CUtensorMap& map_out, const void* in, int n,
+                     cudaStream_t st) {
+  static bool attr_set[64] = {};
+  const int smem = StemPoolSmem::TOTAL + 1024;
+  if (!attr_set[h->device & 63]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[h->device & 63] = true;
+  }
+  StemPoolParams p{};
+  p.in = static_cast<const __nv_bfloat16*>(in);
+  p.weights = h->d_weights + L.w_off;
+  p.bias = h->d_bias + L.b_off;
+  p.n_frames = n;
+  const int bands = n * kSpBandsPerFrame;
+  const int grid = bands < h->num_sms ? bands : h->num_sms;
+  stem_pool_kernel<<<grid, kSpThreads, smem, st>>>(map_out, p);
+  CUDA_TRY(h, cudaGetLastError());
+  h->last_launches++;
+  return 0;
+}
+
 int launch_maxpool(phdfx_t* h, const phdfx_layer_desc& L, const void* in, void* out, int n, cudaStream_t st) {
   const long long total = static_cast<long long>(n) * (out_elems_per_frame(L) / 8);
   const int threads = 256;
@@ -400,8 +432,10 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
     if (L.out_buf == L.in_buf || (L.res_buf >= 0 && L.res_buf == L.out_buf))
       return fail(h, PHDFX_ERR_INVALID, "layer %d: out_buf aliases in_buf or res_buf", i);
     if (L.kind != PHDFX_MAXPOOL) {
-      const Geo g = geometry(L);
-      const int64_t wsz = (L.kind == PHDFX_STEM) ? 7 * 64 * 32 : static_cast<int64_t>(g.K) * L.cout;
+      const Geo g = (L.kind == PHDFX_STEM_POOL) ? Geo{} : geometry(L);
+      const int64_t wsz = (L.kind == PHDFX_STEM || L.kind == PHDFX_STEM_POOL)
+                              ? 7 * 64 * 32
+                              : static_cast<int64_t>(g.K) * L.cout;
       if (L.w_off < 0 || L.w_off + wsz > n_weights || L.b_off < 0 || L.b_off + L.cout > n_bias)
         return fail(h, PHDFX_ERR_INVALID, "layer %d: weight/bias offsets out of range", i);
       if (L.w_off % 8) return fail(h, PHDFX_ERR_INVALID, "layer %d: w_off must be a multiple of 8 elements", i);
@@ -438,6 +472,11 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
     const auto& L = h->layers[i];
     if (L.kind == PHDFX_MAXPOOL) continue;
     if (!h->bufs[L.in_buf]) return fail(h, PHDFX_ERR_INVALID, "layer %d reads buffer %d that no layer writes", i, L.in_buf);
+    if (L.kind == PHDFX_STEM_POOL) {
+      if (int rc = build_stem_pool_map(h, h->bufs[L.out_buf], h->max_frames, &h->maps[i].o)) return rc;
+      h->maps[i].valid = true;
+      continue;
+    }
     if (L.res_buf >= 0 && !h->bufs[L.res_buf])
       return fail(h, PHDFX_ERR_INVALID, "layer %d adds buffer %d that no layer writes", i, L.res_buf);
     if (int rc = build_maps(h, L, h->bufs[L.in_buf], L.res_buf >= 0 ? h->bufs[L.res_buf] : nullptr,
@@ -489,6 +528,11 @@ static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cud
       if (int rc = launch_maxpool(h, L, in, out, n, st)) return rc;
       continue;
     }
+    if (L.kind == PHDFX_STEM_POOL) {
+      const void* src = (L.in_buf == 0 && d_in != nullptr) ? d_in : in;
+      if (int rc = launch_stem_pool(h, L, h->maps[i].o, src, n, st)) return rc;
+      continue;
+    }
     if (L.in_buf == 0 && d_in != nullptr && d_in != h->bufs[0]) {
       // external input buffer: it holds only n frames, so its A map is built per call; the output map over the
       // arena (max_frames extent) is reused
@@ -529,6 +573,11 @@ int phdfx_run_layer(phdfx_t* h, int layer_id, const void* d_in, const void* d_re
   const auto& L = h->layers[layer_id];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (L.kind == PHDFX_MAXPOOL) return launch_maxpool(h, L, d_in, d_out, n, st);
+  if (L.kind == PHDFX_STEM_POOL) {
+    CUtensorMap m;
+    if (int rc = build_stem_pool_map(h, d_out, n, &m)) return rc;
+    return launch_stem_pool(h, L, m, d_in, n, st);
+  }
   if (L.res_buf >= 0 && !d_residual) return fail(h, PHDFX_ERR_INVALID, "layer %d needs a residual input", layer_id);
   LayerMaps tmp;
   const void* res = L.res_buf >= 0 ? d_residual : nullptr;

@@ -7,15 +7,18 @@
 // src/preprocess_resnet_features.py:296 `backbone(x)`).  BN is folded into W and a per-channel fp32 bias
 // on the host, so the epilogue is  y = relu?(acc + bias [+ residual]).
 //
-// Structure: one persistent CTA per SM, 7 warps, warp-specialised.
-//   warp 0   TMA producer   A tile via tiled / im2col / stem-window tensor maps, W tile via a 2-D map, both
-//                           K-major with hardware swizzle, NSTAGE-deep mbarrier ring
-//   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM
-//                           accumulator; tcgen05.commit releases smem slots / publishes the accumulator
-//   warp 2-5 epilogue       per 64-channel group: tcgen05.ld -> + bias (+ residual read from smem) -> ReLU -> bf16,
-//                           written IN PLACE into a 128x128B swizzled staging buffer (conflict-free 16 B accesses)
-//   warp 6   epilogue DMA   one thread: TMA-loads the residual tile into the staging buffer ahead of the epilogue
-//                           warps and TMA-stores the finished buffer; NB buffers, look-ahead kLook groups.
+// Structure: one persistent CTA per SM, 12 warps, warp-specialised.
+//   warp 0    TMA producer   A tile via tiled / im2col / stem-window tensor maps, W tile via a 2-D map, both
+//                            K-major with hardware swizzle, NSTAGE-deep mbarrier ring
+//   warp 1    MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM
+//                            accumulator; tcgen05.commit releases smem slots / publishes the accumulator
+//   warp 2    epilogue DMA   one thread: TMA-loads the residual tile into the staging buffer ahead of the epilogue
+//                            warps and TMA-stores the finished buffer; NB buffers, look-ahead LOOK groups
+//                            (the warp also owns the TMEM allocation)
+//   warp 4-11 epilogue       two warps per TMEM lane quadrant (= two per SM sub-partition, so one hides the other's
+//                            issue latency); per 64-channel group each takes 32 channels: tcgen05.ld -> + bias
+//                            (+ residual read from smem) -> bf16 -> ReLU, written IN PLACE into a 128x128B swizzled
+//                            staging buffer (conflict-free 16 B accesses)
 // All global traffic of the kernel is therefore TMA (full 128 B lines); the only exception is the fused
 // global-average-pool mode, which writes 8 KB of fp32 features per frame directly.
 #pragma once
@@ -47,7 +50,9 @@ struct ConvParams {
 };
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 224;
+constexpr int kNumThreads = 384;
+constexpr int kEpiThreads = 256;   // warps 4..11
+constexpr int kEpiWarps = 8;
 constexpr int kGapRowsPerFrame = 49;
 constexpr int kGapRows = 98;
 constexpr int kStemTileQ = 16, kStemTileP = 8, kStemOut = 112, kStemTilesPerFrame = (112 / 16) * (112 / 8);
@@ -65,7 +70,7 @@ struct ConvCfg {
   static constexpr int NB = (MODE == MODE_GAP) ? 2 : 4;        // epilogue staging buffers
   static constexpr int LOOK = (NB == 2) ? 1 : 2;               // residual loads run LOOK groups ahead of the stores
   static constexpr int GROUPS = BN / kGroupCols;
-  static constexpr int SCRATCH_BYTES = (MODE == MODE_GAP) ? kBlockM * 33 * 4 : 0;
+  static constexpr int SCRATCH_BYTES = (MODE == MODE_GAP) ? 2 * kBlockM * 33 * 4 : 0;
   static constexpr int TAIL_BYTES = 1024 + 2 * BN * 4 + SCRATCH_BYTES;  // barriers + bias double buffer + scratch
   static constexpr int SMEM_MAX = 232448;                              // 227 KB
   static constexpr int NSTAGE_RAW = (SMEM_MAX - 1024 - TAIL_BYTES - NB * kStageOutBytes) / STAGE_BYTES;
@@ -99,9 +104,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   uint64_t* out_full = res_full + NB;                      // [NB] epilogue warps are done with the buffer
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_full + NB);
   float* s_bias = reinterpret_cast<float*>(tail + 1024);   // [2][BN]
-  float* s_scratch = s_bias + 2 * BN;                      // MODE_GAP: [128][33]
+  float* s_scratch = s_bias + 2 * BN;                      // MODE_GAP: [2 halves][128][33]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
 
@@ -109,7 +114,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
   }
-  if (warp == 6 && lane == 0) {
+  if (warp == 2 && lane == 0) {
     if (MODE != MODE_GAP) tma_prefetch_desc(&mapO);
     if (p.has_res) tma_prefetch_desc(&mapR);
   }
@@ -120,11 +125,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], kEpiWarps);  // one arrive per epilogue warp
     }
     for (int i = 0; i < NB; ++i) {
       mbar_init(&res_full[i], 1);
-      mbar_init(&out_full[i], 4);
+      mbar_init(&out_full[i], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -139,7 +144,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -166,25 +171,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_TX + Cfg::B_BYTES);
+          mbar_arrive_expect_tx_elect(&full_bar[stage], Cfg::A_TX + Cfg::B_BYTES);
           if (MODE == MODE_TILED) {
-            tma_load_2d(&mapA, &full_bar[stage], sA, kb * Cfg::BLOCK_K, m_blk * kBlockM);
-            tma_load_2d(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
+            tma_load_2d_elect(&mapA, &full_bar[stage], sA, kb * Cfg::BLOCK_K, m_blk * kBlockM);
+            tma_load_2d_elect(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
           } else if (MODE == MODE_IM2COL) {
             const int tap = kb / p.kb_per_tap;
             const int cb = kb - tap * p.kb_per_tap;
             const int r = tap / p.S;
             const int s = tap - r * p.S;
-            tma_load_im2col_4d(&mapA, &full_bar[stage], sA, cb * Cfg::BLOCK_K, cw, ch, cn,
+            tma_load_im2col_4d_elect(&mapA, &full_bar[stage], sA, cb * Cfg::BLOCK_K, cw, ch, cn,
                                static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-            tma_load_2d(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
+            tma_load_2d_elect(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
           } else if (MODE == MODE_STEM) {
             const int d = kb - 3;  // input row = 2*p + d
-            tma_load_5d(&mapA, &full_bar[stage], sA, 0, cw, d & 1, ch + (d >> 1), cn);
-            tma_load_2d(&mapB, &full_bar[stage], sB, 0, kb * BN);
+            tma_load_5d_elect(&mapA, &full_bar[stage], sA, 0, cw, d & 1, ch + (d >> 1), cn);
+            tma_load_2d_elect(&mapB, &full_bar[stage], sB, 0, kb * BN);
           } else {  // MODE_GAP
-            tma_load_3d(&mapA, &full_bar[stage], sA, kb * Cfg::BLOCK_K, 0, m_blk * 2);
-            tma_load_2d(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
+            tma_load_3d_elect(&mapA, &full_bar[stage], sA, kb * Cfg::BLOCK_K, 0, m_blk * 2);
+            tma_load_2d_elect(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
           }
           if (++stage == NSTAGE) {
             stage = 0;
@@ -195,7 +200,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; one elected lane issues
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -214,22 +219,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
             const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, Cfg::ROWB);
             const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, Cfg::ROWB);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_elect(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          umma_commit_elect(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        umma_commit_elect(&tmem_full[acc]);  // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // ------------------------------------------------------------------ epilogue DMA (one thread)
     if (lane == 0) {
       const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x))
@@ -280,11 +285,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
       if (MODE != MODE_GAP) tma_store_wait_all<0>();
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (warps 4..11)
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;     // which 32 channels of every 64-channel group this warp converts
     const int row = quad * 32 + lane;     // row of the 128-row tile owned by this thread
-    const int et = threadIdx.x - 64;      // 0..127
+    const int et = threadIdx.x - 128;     // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
@@ -294,8 +300,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int n_blk = tile - m_blk * p.n_tiles;
       const int n_base = n_blk * BN;
       float* sb = s_bias + (it & 1) * BN;
-      for (int i = et; i < BN; i += 128) sb[i] = __ldg(&p.bias[n_base + i]);
-      named_barrier_sync(1, 128);
+      for (int i = et; i < BN; i += kEpiThreads) sb[i] = __ldg(&p.bias[n_base + i]);
+      named_barrier_sync(1, kEpiThreads);
 
       bool row_ok = true;
       if (MODE == MODE_GAP) row_ok = (row < kGapRows) && (m_blk * kGapRows + row < p.M);
@@ -309,69 +315,77 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int b = jg % NB;
         mbar_wait(&res_full[b], (jg / NB) & 1);
         uint8_t* row_ptr = stage_out + b * kStageOutBytes + row * 128;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + g * kGroupCols + h * 32, v);
-          tmem_ld_wait();
-          const float4* sb4 = reinterpret_cast<const float4*>(sb + g * kGroupCols + h * 32);
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + g * kGroupCols + half * 32, v);
+        tmem_ld_wait();
+        const float4* sb4 = reinterpret_cast<const float4*>(sb + g * kGroupCols + half * 32);
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            // 16-byte chunk (8 channels) of this thread's row; 128B-swizzle: physical chunk = logical ^ (row & 7)
-            uint4* sp = reinterpret_cast<uint4*>(row_ptr + (((h * 4 + c4) ^ (row & 7)) << 4));
-            const float4 b0 = sb4[2 * c4], b1 = sb4[2 * c4 + 1];
-            float f[8];
-            f[0] = __uint_as_float(v[8 * c4 + 0]) + b0.x;
-            f[1] = __uint_as_float(v[8 * c4 + 1]) + b0.y;
-            f[2] = __uint_as_float(v[8 * c4 + 2]) + b0.z;
-            f[3] = __uint_as_float(v[8 * c4 + 3]) + b0.w;
-            f[4] = __uint_as_float(v[8 * c4 + 4]) + b1.x;
-            f[5] = __uint_as_float(v[8 * c4 + 5]) + b1.y;
-            f[6] = __uint_as_float(v[8 * c4 + 6]) + b1.z;
-            f[7] = __uint_as_float(v[8 * c4 + 7]) + b1.w;
-            if (p.has_res) {
-              const uint4 rv = *sp;
-              f[0] += bf16_lo(rv.x);
-              f[1] += bf16_hi(rv.x);
-              f[2] += bf16_lo(rv.y);
-              f[3] += bf16_hi(rv.y);
-              f[4] += bf16_lo(rv.z);
-              f[5] += bf16_hi(rv.z);
-              f[6] += bf16_lo(rv.w);
-              f[7] += bf16_hi(rv.w);
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
-            if (MODE == MODE_GAP) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) s_scratch[row * 33 + c4 * 8 + j] = row_ok ? f[j] : 0.0f;
-            } else {
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              *sp = o;
-            }
+        for (int c4 = 0; c4 < 4; ++c4) {
+          // 16-byte chunk (8 channels) of this thread's row; 128B-swizzle: physical chunk = logical ^ (row & 7)
+          uint4* sp = reinterpret_cast<uint4*>(row_ptr + (((half * 4 + c4) ^ (row & 7)) << 4));
+          const float4 b0 = sb4[2 * c4], b1 = sb4[2 * c4 + 1];
+          float f[8];
+          f[0] = __uint_as_float(v[8 * c4 + 0]) + b0.x;
+          f[1] = __uint_as_float(v[8 * c4 + 1]) + b0.y;
+          f[2] = __uint_as_float(v[8 * c4 + 2]) + b0.z;
+          f[3] = __uint_as_float(v[8 * c4 + 3]) + b0.w;
+          f[4] = __uint_as_float(v[8 * c4 + 4]) + b1.x;
+          f[5] = __uint_as_float(v[8 * c4 + 5]) + b1.y;
+          f[6] = __uint_as_float(v[8 * c4 + 6]) + b1.z;
+          f[7] = __uint_as_float(v[8 * c4 + 7]) + b1.w;
+          if (p.has_res) {
+            const uint4 rv = *sp;
+            f[0] += bf16_lo(rv.x);
+            f[1] += bf16_hi(rv.x);
+            f[2] += bf16_lo(rv.y);
+            f[3] += bf16_hi(rv.y);
+            f[4] += bf16_lo(rv.z);
+            f[5] += bf16_hi(rv.z);
+            f[6] += bf16_lo(rv.w);
+            f[7] += bf16_hi(rv.w);
           }
           if (MODE == MODE_GAP) {
-            // deterministic in-CTA mean over the 49 rows of each of the tile's two frames
-            named_barrier_sync(2, 128);
-            if (et < 64) {
-              const int fr = et >> 5;
-              const int col = et & 31;
-              const int frame = m_blk * 2 + fr;
-              float acc_sum = 0.0f;
-              for (int r = 0; r < kGapRowsPerFrame; ++r)
-                acc_sum += s_scratch[(fr * kGapRowsPerFrame + r) * 33 + col];
-              if (frame < p.n_frames)
-                p.feats[static_cast<size_t>(frame) * p.Cout + n_base + g * kGroupCols + h * 32 + col] =
-                    acc_sum * (1.0f / kGapRowsPerFrame);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = p.relu ? fmaxf(f[j], 0.0f) : f[j];
+              s_scratch[(half * kBlockM + row) * 33 + c4 * 8 + j] = row_ok ? x : 0.0f;
             }
-            named_barrier_sync(3, 128);
+          } else {
+            // round once to bf16, ReLU on the packed pairs (max commutes with the rounding)
+            __nv_bfloat162 o2[4];
+            o2[0] = __floats2bfloat162_rn(f[0], f[1]);
+            o2[1] = __floats2bfloat162_rn(f[2], f[3]);
+            o2[2] = __floats2bfloat162_rn(f[4], f[5]);
+            o2[3] = __floats2bfloat162_rn(f[6], f[7]);
+            if (p.relu) {
+              const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o2[j] = __hmax2(o2[j], z);
+            }
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&o2[0]);
+            o.y = *reinterpret_cast<uint32_t*>(&o2[1]);
+            o.z = *reinterpret_cast<uint32_t*>(&o2[2]);
+            o.w = *reinterpret_cast<uint32_t*>(&o2[3]);
+            *sp = o;
           }
+        }
+        if (MODE == MODE_GAP) {
+          // deterministic in-CTA mean over the 49 rows of each of the tile's two frames
+          named_barrier_sync(2, kEpiThreads);
+          if (et < 128) {
+            const int hh = et >> 6;          // which 32-channel half
+            const int fr = (et >> 5) & 1;    // which of the tile's two frames
+            const int col = et & 31;
+            const int frame = m_blk * 2 + fr;
+            float acc_sum = 0.0f;
+            for (int r = 0; r < kGapRowsPerFrame; ++r)
+              acc_sum += s_scratch[(hh * kBlockM + fr * kGapRowsPerFrame + r) * 33 + col];
+            if (frame < p.n_frames)
+              p.feats[static_cast<size_t>(frame) * p.Cout + n_base + g * kGroupCols + hh * 32 + col] =
+                  acc_sum * (1.0f / kGapRowsPerFrame);
+          }
+          named_barrier_sync(3, kEpiThreads);
         }
         // hand the buffer to the DMA thread (generic-proxy writes -> async proxy)
         if (MODE != MODE_GAP) fence_proxy_async_smem();

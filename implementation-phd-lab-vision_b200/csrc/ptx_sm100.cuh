@@ -171,6 +171,90 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- warp-uniform issue: every lane of the (converged) warp executes the statement, one elected lane performs it.
+// Keeping the surrounding control flow warp-uniform lets ptxas hold descriptors / coordinates in uniform registers
+// instead of wrapping each UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST loop.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_elect(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                  int c2) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_elect(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                  int c2, int c3, int c4) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_elect(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w,
+                                                         int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2], {%7, %8};\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+// warp index that ptxas can treat as warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are `row_bytes` (64 or 128) wide and
 // stored densely with the matching TMA swizzle (SWIZZLE_64B / SWIZZLE_128B): 8-row groups are

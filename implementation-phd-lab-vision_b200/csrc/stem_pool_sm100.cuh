@@ -1,0 +1,350 @@
+// K2: stem conv 7x7/2 (3->64) + folded BN + ReLU + MaxPool 3x3/2, one kernel (torchvision models/resnet.py:197-200,
+// :268-271: conv1, bn1, relu, maxpool).  Input NHWC4p bf16 [N][224][232][4], output NHWC bf16 [N][56][56][64].
+//
+// The conv output (1.6 MB/frame) never leaves the SM.  Each CTA walks a band of conv rows of one frame, two conv rows
+// (= one pooled row) per step.
+//
+// Implicit GEMM without any im2col copy: one conv row = one 128x64 MMA tile (112 valid pixels).  For filter row r the
+// A operand is the RAW input row 2p+r-3 as it lies in shared memory: output column q reads the 8-pixel x 4-channel
+// window starting 16*q bytes into the row, i.e. a K-major no-swizzle operand whose rows OVERLAP (row stride 16 B,
+// K-chunk stride LBO = 16 B, 8-row-group stride SBO = 128 B) — the tensor core does the sliding window.  Rows outside
+// the image read a zeroed slot.  K = 7 filter rows x 32 (8 px x 4 ch; tap -1 and channel 3 carry zero weights).
+//   warp 0    producer: cp.async.bulk of input row PAIRS into an 8-slot ring (2 x 1856 B per slot)
+//   warp 1    MMA issuer: 14 tcgen05.mma (M=128, N=64, K=16) per conv row, weights resident in smem (28 KB);
+//             a step's even/odd conv rows go to adjacent 64-column halves of one of two TMEM buffers
+//   warp 2    DMA: TMA store of pooled rows (56 px x 64 ch = 7 KB each); owns the TMEM allocation
+//   warp 4-11 epilogue, two warps per TMEM lane quadrant (32 channels each).  Thread q owns conv column q:
+//             vertical 3-max of rows 2i-1, 2i, 2i+1 in REGISTERS (row 2i-1 is carried from the previous step), the
+//             result goes to a swizzled smem row, then the horizontal 3-max (columns 2j-1..2j+1) + store staging.
+//             No ReLU instruction anywhere: the horizontal max starts at 0 and max(0, max(v)) == max-pool(relu(v)).
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace phdfxk {
+
+constexpr int kSpIn = 224, kSpInPitchPx = 232, kSpOut = 112, kSpPool = 56;
+constexpr int kSpRowBytes = kSpInPitchPx * 8;   // 1856
+constexpr int kSpRowPitch = 2048;               // smem pitch of one input row
+constexpr int kSpPairSlots = 8;                 // ring of row pairs
+constexpr int kSpBand = 16;                     // conv rows per work item
+constexpr int kSpBandsPerFrame = kSpOut / kSpBand;  // 7
+constexpr int kSpConvRowBytes = kSpOut * 128;   // 14336: one conv row, 112 px x 64 ch bf16
+constexpr int kSpPoolRowBytes = 8192;           // staging pitch (56 x 128 B = 7168 used)
+constexpr int kSpWeightBytes = 7 * 4096;        // [7][4 k-chunks][64 cout][8] bf16
+constexpr int kSpThreads = 384;
+constexpr int kSpEpiThreads = 256;
+constexpr int kSpEpiWarps = 8;
+
+struct StemPoolSmem {
+  static constexpr int RING = 0;                                           // 8 x 4096
+  static constexpr int ZERO = RING + kSpPairSlots * 2 * kSpRowPitch;       // 2048 + 256 zero bytes
+  static constexpr int WEIGHTS = ZERO + kSpRowPitch + 1024;                // 1024-aligned
+  static constexpr int CONV = WEIGHTS + kSpWeightBytes;                    // 2 x 14336 vertical-max rows, 1024-aligned
+  static constexpr int POOL = CONV + 2 * kSpConvRowBytes;                  // 2 x 8192
+  static constexpr int BIAS = POOL + 2 * kSpPoolRowBytes;                  // 64 floats
+  static constexpr int BARS = BIAS + 256;
+  static constexpr int TOTAL = BARS + 512;
+};
+static_assert(StemPoolSmem::WEIGHTS % 1024 == 0 && StemPoolSmem::CONV % 1024 == 0 && StemPoolSmem::POOL % 1024 == 0,
+              "swizzled regions must be 1024-byte aligned");
+
+struct StemPoolParams {
+  const __nv_bfloat16* in;       // NHWC4p
+  const __nv_bfloat16* weights;  // pre-laid-out smem image, kSpWeightBytes
+  const float* bias;             // [64]
+  int n_frames;
+};
+
+// executed by a whole converged warp; one elected lane issues (keeps operands in uniform registers)
+__device__ __forceinline__ void bulk_load_elect(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// no-swizzle K-major descriptor: LBO = K-chunk (8 elements) stride, SBO = 8-row-group stride
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (static_cast<uint64_t>((addr & 0x3FFFFu) >> 4)) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+         (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
+}
+
+// band b of this launch -> (frame, first conv row computed, first conv row whose pooled output is emitted)
+struct Band {
+  int n, p0, p_first, p_last, j_first, j_last;
+  __device__ __forceinline__ explicit Band(int b) {
+    n = b / kSpBandsPerFrame;
+    p0 = (b - n * kSpBandsPerFrame) * kSpBand;
+    p_first = p0 > 0 ? p0 - 1 : 0;  // one halo conv row: pooled row p0/2 needs conv row p0-1
+    p_last = p0 + kSpBand - 1;
+    j_first = p_first - 2 < 0 ? 0 : p_first - 2;                       // input row pairs p-2 .. p+1 feed conv row p
+    j_last = p_last + 1 > kSpOut - 1 ? kSpOut - 1 : p_last + 1;
+  }
+  __device__ __forceinline__ int pairs() const { return j_last - j_first + 1; }
+};
+
+__global__ void __launch_bounds__(kSpThreads, 1)
+stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using L = StemPoolSmem;
+  uint64_t* pair_full = reinterpret_cast<uint64_t*>(smem + L::BARS);  // [8]
+  uint64_t* pair_empty = pair_full + kSpPairSlots;                   // [8]
+  uint64_t* tmem_full = pair_empty + kSpPairSlots;                   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                              // [2]
+  uint64_t* pool_full = tmem_empty + 2;                              // [2]
+  uint64_t* pool_free = pool_full + 2;                               // [2]
+  uint64_t* w_full = pool_free + 2;                                  // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_full + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + L::BIAS);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int num_bands = p.n_frames * kSpBandsPerFrame;
+
+  // zero slot, bias
+  for (int i = threadIdx.x; i < (kSpRowPitch + 1024) / 16; i += kSpThreads)
+    reinterpret_cast<uint4*>(smem + L::ZERO)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = __ldg(&p.bias[threadIdx.x]);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kSpPairSlots; ++i) {
+      mbar_init(&pair_full[i], 1);
+      mbar_init(&pair_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kSpEpiWarps);
+      mbar_init(&pool_full[i], kSpEpiWarps);
+      mbar_init(&pool_free[i], 1);
+    }
+    mbar_init(w_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2 && lane == 0) tma_prefetch_desc(&mapO);
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();  // zero slot is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer (whole warp, uniform flow)
+    {
+      mbar_arrive_expect_tx_elect(w_full, kSpWeightBytes);
+      bulk_load_elect(smem + L::WEIGHTS, p.weights, kSpWeightBytes, w_full);
+      int seq = 0;
+      for (int b = blockIdx.x; b < num_bands; b += gridDim.x) {
+        const Band band(b);
+        const uint8_t* frame = reinterpret_cast<const uint8_t*>(p.in) +
+                               static_cast<size_t>(band.n) * kSpIn * kSpRowBytes;
+        for (int j = band.j_first; j <= band.j_last; ++j, ++seq) {
+          const int slot = seq % kSpPairSlots;
+          mbar_wait(&pair_empty[slot], ((seq / kSpPairSlots) & 1) ^ 1);
+          uint8_t* dst = smem + L::RING + slot * 2 * kSpRowPitch;
+          mbar_arrive_expect_tx_elect(&pair_full[slot], 2 * kSpRowBytes);
+          bulk_load_elect(dst, frame + static_cast<size_t>(2 * j) * kSpRowBytes, kSpRowBytes, &pair_full[slot]);
+          bulk_load_elect(dst + kSpRowPitch, frame + static_cast<size_t>(2 * j + 1) * kSpRowBytes, kSpRowBytes,
+                          &pair_full[slot]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, uniform flow)
+    {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+      const uint32_t ring_addr = smem_u32(smem + L::RING);
+      const uint32_t zero_addr = smem_u32(smem + L::ZERO);
+      const uint32_t w_addr = smem_u32(smem + L::WEIGHTS);
+      mbar_wait(w_full, 0);
+      int buf = 0;  // TMEM buffer of the current step: columns [buf*128, +64) even row, [buf*128+64, +64) odd row
+      uint32_t buf_phase = 0;
+      int seq_base = 0;
+      for (int b = blockIdx.x; b < num_bands; b += gridDim.x) {
+        const Band band(b);
+        int waited = band.j_first;  // first pair of this band not yet known to have landed
+        for (int pr = band.p_first; pr <= band.p_last; ++pr) {
+          // a step = (even row, odd row); the band's halo row (odd) is a step of its own
+          if (!(pr & 1) || pr == band.p_first) mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
+          // input row pairs pr-2 .. pr+1 feed this conv row; earlier ones were already waited for
+          const int need = pr + 1 > band.j_last ? band.j_last : pr + 1;
+          for (; waited <= need; ++waited) {
+            const int seq = seq_base + (waited - band.j_first);
+            mbar_wait(&pair_full[seq % kSpPairSlots], (seq / kSpPairSlots) & 1);
+          }
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * 128 + (pr & 1) * 64;
+#pragma unroll
+          for (int r = 0; r < 7; ++r) {
+            const int h = 2 * pr + r - 3;
+            uint32_t a_row = zero_addr;
+            if (h >= 0 && h < kSpIn) {
+              const int seq = seq_base + ((h >> 1) - band.j_first);
+              a_row = ring_addr + (seq % kSpPairSlots) * 2 * kSpRowPitch + (h & 1) * kSpRowPitch;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t adesc = make_nosw_desc(a_row + k * 32, 16, 128);
+              const uint64_t bdesc = make_nosw_desc(w_addr + r * 4096 + k * 2048, 1024, 128);
+              umma_bf16_elect(d_tmem, adesc, bdesc, idesc, (r | k) != 0 ? 1u : 0u);
+            }
+          }
+          if (pr & 1) {
+            umma_commit_elect(&tmem_full[buf]);
+            buf ^= 1;
+            if (buf == 0) buf_phase ^= 1;
+          }
+          // pair pr-2 is not needed by later rows
+          if (pr - 2 >= band.j_first) {
+            const int seq = seq_base + (pr - 2 - band.j_first);
+            umma_commit_elect(&pair_empty[seq % kSpPairSlots]);
+          }
+          if (pr == band.p_last) {
+            for (int j = (pr - 1 < band.j_first ? band.j_first : pr - 1); j <= band.j_last; ++j) {
+              const int seq = seq_base + (j - band.j_first);
+              umma_commit_elect(&pair_empty[seq % kSpPairSlots]);
+            }
+          }
+        }
+        seq_base += band.pairs();
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ DMA: pooled rows out
+    if (lane == 0) {
+      int k = 0;  // pooled rows stored so far
+      for (int b = blockIdx.x; b < num_bands; b += gridDim.x) {
+        const Band band(b);
+        for (int i = band.p0 / 2; i < (band.p0 + kSpBand) / 2; ++i, ++k) {
+          const int buf = k & 1;
+          mbar_wait(&pool_full[buf], (k >> 1) & 1);
+          tma_store_2d(&mapO, smem + L::POOL + buf * kSpPoolRowBytes, 0, (band.n * kSpPool + i) * kSpPool);
+          tma_store_commit();
+          if (k >= 1) {
+            tma_store_wait_read<1>();          // store k-1 has left smem
+            mbar_arrive(&pool_free[(k - 1) & 1]);
+          }
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue + pool (warps 4..11)
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;  // 32-channel half of the 64 output channels
+    const int q = quad * 32 + lane;    // conv output column owned by this thread (TMEM lane)
+    const int et = threadIdx.x - 128;  // 0..255
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + half * 32;
+    const float4* sb4 = reinterpret_cast<const float4*>(s_bias + half * 32);
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    int k = 0;  // pooled rows produced so far
+    // conv row (+bias, bf16x2-packed) of this thread's column and channel half
+    auto load_row = [&](uint32_t taddr, __nv_bfloat162 (&dst)[16]) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 bb = sb4[c];
+        dst[2 * c + 0] = __floats2bfloat162_rn(__uint_as_float(v[4 * c + 0]) + bb.x, __uint_as_float(v[4 * c + 1]) + bb.y);
+        dst[2 * c + 1] = __floats2bfloat162_rn(__uint_as_float(v[4 * c + 2]) + bb.z, __uint_as_float(v[4 * c + 3]) + bb.w);
+      }
+    };
+    for (int b = blockIdx.x; b < num_bands; b += gridDim.x) {
+      const Band band(b);
+      __nv_bfloat162 carry[16];  // conv row 2i-1 of the next pooled row i
+      bool have_carry = false;
+      if (band.p_first & 1) {
+        // halo step: conv row p0-1 only
+        mbar_wait(&tmem_full[buf], buf_phase);
+        tc_fence_after();
+        load_row(t_lane + buf * 128 + 64, carry);
+        have_carry = true;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        buf ^= 1;
+        if (buf == 0) buf_phase ^= 1;
+      }
+      for (int i = band.p0 / 2; i < (band.p0 + kSpBand) / 2; ++i, ++k) {
+        mbar_wait(&tmem_full[buf], buf_phase);
+        tc_fence_after();
+        __nv_bfloat162 ev[16], od[16];
+        load_row(t_lane + buf * 128, ev);       // conv row 2i
+        load_row(t_lane + buf * 128 + 64, od);  // conv row 2i+1
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        buf ^= 1;
+        if (buf == 0) buf_phase ^= 1;
+        // vertical 3-max in registers
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat162 m = __hmax2(ev[j], od[j]);
+          if (have_carry) m = __hmax2(m, carry[j]);
+          carry[j] = od[j];
+          ev[j] = m;
+        }
+        have_carry = true;
+        uint8_t* vrow = smem + L::CONV + (k & 1) * kSpConvRowBytes;
+        if (q < kSpOut) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&ev[4 * c4 + 0]);
+            o.y = *reinterpret_cast<uint32_t*>(&ev[4 * c4 + 1]);
+            o.z = *reinterpret_cast<uint32_t*>(&ev[4 * c4 + 2]);
+            o.w = *reinterpret_cast<uint32_t*>(&ev[4 * c4 + 3]);
+            *reinterpret_cast<uint4*>(vrow + q * 128 + (((half * 4 + c4) ^ (q & 7)) << 4)) = o;
+          }
+        }
+        named_barrier_sync(1, kSpEpiThreads);  // the vertical-max row is complete
+        // horizontal 3-max (columns 2j-1 .. 2j+1, >= 0) starting from 0: the 0 is both the ReLU and the -inf padding
+        // of the reference's MaxPool2d (its input is post-ReLU, resnet.py:270-271)
+        const int pbuf = k & 1;
+        if (k >= 2) mbar_wait(&pool_free[pbuf], ((k >> 1) - 1) & 1);
+        uint8_t* pool_row = smem + L::POOL + pbuf * kSpPoolRowBytes;
+        for (int task = et; task < kSpPool * 8; task += kSpEpiThreads) {
+          const int j = task >> 3;
+          const int c = task & 7;
+          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+          __nv_bfloat162 m[4] = {z, z, z, z};
+#pragma unroll
+          for (int dc = 0; dc < 3; ++dc) {
+            const int col = 2 * j - 1 + dc;
+            if (col < 0) continue;
+            const uint4 val = *reinterpret_cast<const uint4*>(vrow + col * 128 + ((c ^ (col & 7)) << 4));
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) m[t] = __hmax2(m[t], pv[t]);
+          }
+          uint4 o;
+          o.x = *reinterpret_cast<uint32_t*>(&m[0]);
+          o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+          o.z = *reinterpret_cast<uint32_t*>(&m[2]);
+          o.w = *reinterpret_cast<uint32_t*>(&m[3]);
+          *reinterpret_cast<uint4*>(pool_row + j * 128 + ((c ^ (j & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pool_full[pbuf]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace phdfxk

@@ -28,7 +28,7 @@ EXPORTS = [
     "phdfx_last_launch_count",
 ]
 
-PHDFX_CONV, PHDFX_STEM, PHDFX_MAXPOOL = 0, 1, 2
+PHDFX_CONV, PHDFX_STEM, PHDFX_MAXPOOL, PHDFX_STEM_POOL = 0, 1, 2, 3
 IMG, IN_WPAD, IN_LPAD, IN_CPAD, FEAT_DIM = 224, 232, 4, 4, 2048
 
 

@@ -23,7 +23,8 @@ from .weights import Plan, build_plan
 class B200Backbone:
     FEAT_DIM = _lib.FEAT_DIM
 
-    def __init__(self, backbone: nn.Module, device: "int | str | torch.device" = 0, max_frames: int = 1280):
+    def __init__(self, backbone: nn.Module, device: "int | str | torch.device" = 0, max_frames: int = 1280,
+                 fuse_stem_pool: bool = True):
         self._lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("B200Backbone needs a CUDA device (sm_100); this backend has no CPU fallback")
@@ -32,7 +33,7 @@ class B200Backbone:
             raise RuntimeError(f"B200Backbone cannot run on {dev}; this backend has no CPU fallback")
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.max_frames = int(max_frames)
-        self.plan: Plan = build_plan(backbone)
+        self.plan: Plan = build_plan(backbone, fuse_stem_pool=fuse_stem_pool)
         self._h = C.c_void_p()
         _lib.check(self._lib.phdfx_create(C.byref(self._h), self.device.index, self.max_frames))
         arr = (_lib.LayerDesc * len(self.plan.layers))(*self.plan.layers)
@@ -165,7 +166,9 @@ class B200Backbone:
         L = self.plan.layers[layer_id]
         n = x.shape[0]
         self._check_dev(x, "x")
-        if L.kind == _lib.PHDFX_MAXPOOL:
+        if L.kind == _lib.PHDFX_STEM_POOL:
+            out = torch.empty(n, 56, 56, L.cout, device=self.device, dtype=torch.bfloat16)
+        elif L.kind == _lib.PHDFX_MAXPOOL:
             ho = (L.hin + 2 - 3) // 2 + 1
             out = torch.empty(n, ho, ho, L.cout, device=self.device, dtype=torch.bfloat16)
         else:

@@ -17,7 +17,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
-from ._lib import PHDFX_CONV, PHDFX_MAXPOOL, PHDFX_STEM, LayerDesc
+from ._lib import PHDFX_CONV, PHDFX_MAXPOOL, PHDFX_STEM, PHDFX_STEM_POOL, LayerDesc
 
 _ALIGN = 64  # elements; keeps every layer's weight block 128-byte aligned for TMA
 
@@ -58,6 +58,17 @@ def pack_stem(w: torch.Tensor) -> torch.Tensor:
     return out.to(torch.bfloat16).reshape(-1)
 
 
+def pack_stem_pool(w: torch.Tensor) -> torch.Tensor:
+    """[64, 3, 7, 7] fp32 -> flat bf16 [7 (filter row)][4 (k-chunk)][64 (cout)][8]: the shared-memory image of the
+    fused stem kernel's B operand (K-major, no swizzle: 8x16 B core matrices, k-chunk stride 1024 B);
+    k = chunk*8 + e = (s+1)*4 + c."""
+    cout, cin, r, s = w.shape
+    assert (cout, cin, r, s) == (64, 3, 7, 7), w.shape
+    out = torch.zeros(7, 64, 8, 4, dtype=torch.float32)
+    out[:, :, 1:8, 0:3] = w.permute(2, 0, 3, 1)
+    return out.reshape(7, 64, 4, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16).reshape(-1)
+
+
 def _children(backbone: nn.Module):
     """(conv1, bn1, maxpool, [layer1..4]) from the reference's Sequential or a torchvision ResNet."""
     if isinstance(backbone, nn.Sequential):
@@ -69,7 +80,9 @@ def _children(backbone: nn.Module):
                                                             backbone.layer4]
 
 
-def build_plan(backbone: nn.Module) -> Plan:
+def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True) -> Plan:
+    """fuse_stem_pool=True (default): conv1+bn1+relu+maxpool is ONE launch (stem_pool_sm100.cuh).  False keeps the
+    separate implicit-GEMM stem and max-pool kernels (used for A/B measurements and their own parity tests)."""
     conv1, bn1, maxpool, stages = _children(backbone)
     chunks, biases, layers, names = [], [], [], []
     w_cursor = 0
@@ -98,13 +111,19 @@ def build_plan(backbone: nn.Module) -> Plan:
 
     # stem: conv1 + bn1 + relu (resnet.py:268-270), then maxpool (:271)
     w, b = fold_conv_bn(conv1, bn1)
-    w_off, b_off = add_weights(pack_stem(w), b)
-    layers.append(desc(kind=PHDFX_STEM, cin=3, cout=64, r=7, s=7, stride=2, pad=3, hin=224, win=224, relu=1,
-                       in_buf=0, out_buf=1, w_off=w_off, b_off=b_off))
-    names.append("conv1")
-    layers.append(desc(kind=PHDFX_MAXPOOL, cin=64, cout=64, r=3, s=3, stride=2, pad=1, hin=112, win=112, in_buf=1,
-                       out_buf=2))
-    names.append("maxpool")
+    if fuse_stem_pool:
+        w_off, b_off = add_weights(pack_stem_pool(w), b)
+        layers.append(desc(kind=PHDFX_STEM_POOL, cin=3, cout=64, r=7, s=7, stride=2, pad=3, hin=224, win=224,
+                           relu=1, in_buf=0, out_buf=2, w_off=w_off, b_off=b_off))
+        names.append("conv1+maxpool")
+    else:
+        w_off, b_off = add_weights(pack_stem(w), b)
+        layers.append(desc(kind=PHDFX_STEM, cin=3, cout=64, r=7, s=7, stride=2, pad=3, hin=224, win=224, relu=1,
+                           in_buf=0, out_buf=1, w_off=w_off, b_off=b_off))
+        names.append("conv1")
+        layers.append(desc(kind=PHDFX_MAXPOOL, cin=64, cout=64, r=3, s=3, stride=2, pad=1, hin=112, win=112,
+                           in_buf=1, out_buf=2))
+        names.append("maxpool")
 
     x_buf, o_buf = 2, 1  # block input / block output ping-pong; 3, 4, 5 = conv1 out, conv2 out, downsample out
     h = 56

@@ -105,7 +105,7 @@ def main():
     def want(i, L):
         if L.kind == 2:
             return group == "pool"
-        if L.kind == 1:
+        if L.kind in (1, 3):
             return group == "stem"
         if L.gap:
             return group == "gap"
@@ -123,7 +123,7 @@ def main():
             seen.add(key)
             case = {"layer": i, "name": name, **L.as_dict()}
             try:
-                if L.kind == 1:
+                if L.kind in (1, 3):
                     x = torch.randn(n, 3, 224, 224, device="cuda", generator=g)
                     xin = to_nhwc4p(x)
                     x_ref = x.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()

@@ -100,7 +100,7 @@ def test_preprocess_whole_frame_when_no_boxes(eng):
 
 # ------------------------------------------------------------------------------------------------ per-layer
 def _layer_modules(bb):
-    out = {"conv1": (bb[0], bb[1])}
+    out = {"conv1": (bb[0], bb[1]), "conv1+maxpool": (bb[0], bb[1])}
     for li in range(4):
         for bi, blk in enumerate(bb[4 + li]):
             p = f"layer{li + 1}.{bi}"
@@ -139,7 +139,7 @@ def test_every_layer_shape_vs_fp32_torch(eng, backbone, n):
         conv, bn = mods[name]
         w, b = phdfx.fold_conv_bn(conv, bn)
         w = w.to(torch.bfloat16).float().cuda()
-        if L.kind == 1:
+        if L.kind in (1, 3):
             x_nchw = torch.randn(n, 3, 224, 224, device="cuda", generator=g)
             x_in = torch.zeros(n, 224, 232, 4, device="cuda", dtype=torch.bfloat16)
             x_in[:, :, 4:228, :3] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
@@ -157,6 +157,8 @@ def test_every_layer_shape_vs_fp32_torch(eng, backbone, n):
             ref = ref + res.float().permute(0, 3, 1, 2)
         if L.relu:
             ref = torch.relu(ref)
+        if L.kind == 3:  # fused stem: the conv output is rounded to bf16 before the max-pool
+            ref = F.max_pool2d(ref, 3, 2, 1)
         if L.gap:
             ref = ref.mean(dim=(2, 3))
             tol = 1e-4  # fp32 in, fp32 out
@@ -166,7 +168,27 @@ def test_every_layer_shape_vs_fp32_torch(eng, backbone, n):
         err = (got.float() - ref).abs().max().item() / ref.abs().max().item()
         assert err < tol, f"{name}: normalised error {err}"
         checked += 1
-    assert checked >= 26
+    assert checked >= 25
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_unfused_stem_and_maxpool_kernels(backbone, n):
+    """The separate implicit-GEMM stem and max-pool kernels (fuse_stem_pool=False) and the fused kernel agree
+    bit-for-bit on the whole path."""
+    fused = phdfx.B200Backbone(backbone, device=0, max_frames=4)
+    unfused = phdfx.B200Backbone(backbone, device=0, max_frames=4, fuse_stem_pool=False)
+    frames = torch.from_numpy(R.seeded_frames(n, 224, 224, 31)).cuda()
+    a = fused.extract_u8(frames, None)
+    b = unfused.extract_u8(frames, None)
+    assert fused.launches == 54 and unfused.launches == 55
+    assert torch.equal(a, b)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.relu(torch.randn(n, 112, 112, 64, device="cuda", generator=g)).to(torch.bfloat16)
+    got = unfused.run_layer(1, x)
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(got.float(), ref)
+    fused.close()
+    unfused.close()
 
 
 # ------------------------------------------------------------------------------------------------ whole path
@@ -292,7 +314,7 @@ def test_full_batch_256_properties():
     e = phdfx.B200Backbone(bb, device=0, max_frames=256)
     frames = torch.from_numpy(R.seeded_frames(256, 224, 224, 13)).cuda()
     big = e.extract_u8(frames, None)
-    assert e.launches == 55  # K1 + 53 convs + maxpool, all ours
+    assert e.launches == 54  # K1 + fused stem/maxpool + 52 convs, all ours
     small = torch.cat([e.extract_u8(frames[i:i + 37].contiguous(), None) for i in range(0, 256, 37)])
     assert torch.equal(big, small)
     assert torch.isfinite(big).all()

@@ -30,10 +30,12 @@ def test_fold_is_exact_in_fp32(backbone):
         assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
 
 
-def test_plan_structure(plan):
+def test_plan_structure(plan, backbone):
     kinds = [l.kind for l in plan.layers]
-    assert kinds[0] == 1 and kinds[1] == 2 and kinds.count(0) == 52  # stem, maxpool, 52 bottleneck convs
-    assert len(plan.layers) == 54 and plan.names[-1] == "layer4.2.conv3"
+    assert kinds[0] == 3 and kinds.count(0) == 52  # fused stem+maxpool, 52 bottleneck convs
+    assert len(plan.layers) == 53 and plan.names[-1] == "layer4.2.conv3"
+    unfused = phdfx.build_plan(backbone, fuse_stem_pool=False)
+    assert [l.kind for l in unfused.layers[:2]] == [1, 2] and len(unfused.layers) == 54
     assert sum(l.gap for l in plan.layers) == 1 and plan.layers[-1].gap == 1
     # 16 conv3 with residual, 4 downsample without relu
     assert sum(1 for l in plan.layers if l.res_buf >= 0) == 16
@@ -62,6 +64,8 @@ def test_dataflow_is_consistent(plan):
         h, c = shape[l.in_buf]
         assert (h, c) == (l.hin, l.cin), name
         ho = (l.hin + 2 * l.pad - l.r) // l.stride + 1
+        if l.kind == 3:
+            ho = 56
         if l.res_buf >= 0:
             assert shape[l.res_buf] == (ho, l.cout), name
         shape[l.out_buf] = (ho, l.cout)
@@ -85,6 +89,20 @@ def test_pack_stem_layout():
     for r in (0, 3, 6):
         for s in (0, 2, 6):
             assert torch.equal(p[r, :, s + 1, :3], wb[:, :, r, s])
+
+
+def test_pack_stem_pool_layout():
+    w = torch.randn(64, 3, 7, 7)
+    p = phdfx.pack_stem_pool(w).to(torch.float32).reshape(7, 4, 64, 8)  # [r][k-chunk][cout][e], k = chunk*8 + e
+    wb = w.to(torch.bfloat16).to(torch.float32)
+    for r in (0, 2, 6):
+        for s in (0, 3, 6):
+            for c in range(3):
+                k = (s + 1) * 4 + c
+                assert torch.equal(p[r, k // 8, :, k % 8], wb[:, c, r, s])
+    # tap -1 (k = 0..3) and the padding channel carry zero weights
+    assert torch.count_nonzero(p[:, 0, :, 0:4]) == 0
+    assert torch.count_nonzero(p.reshape(7, 4, 64, 2, 4)[..., 3]) == 0
 
 
 def test_packed_weights_reproduce_the_network(backbone, plan):

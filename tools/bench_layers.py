@@ -31,7 +31,7 @@ def main():
     rows = []
     tot_ms = 0.0
     for i, (name, L) in enumerate(zip(eng.plan.names, eng.plan.layers)):
-        if L.kind == 1:
+        if L.kind in (1, 3):
             x = torch.zeros(n, 224, 232, 4, device="cuda", dtype=torch.bfloat16)
             x[:, :, 4:228, :3] = torch.randn(n, 224, 224, 3, device="cuda", generator=g).to(torch.bfloat16)
             in_bytes = n * 224 * 232 * 4 * 2
@@ -43,6 +43,8 @@ def main():
         if L.res_buf >= 0:
             res = torch.randn(n, ho, ho, L.cout, device="cuda", generator=g).to(torch.bfloat16)
         out_bytes = n * ho * ho * L.cout * 2 if not L.gap else n * L.cout * 4
+        if L.kind == 3:
+            out_bytes = n * 56 * 56 * 64 * 2
         w_bytes = 0 if L.kind == 2 else (L.r * L.s * L.cin * L.cout * 2)
         macs = 0 if L.kind == 2 else n * ho * ho * L.cout * L.cin * L.r * L.s
         alg_bytes = in_bytes + out_bytes + (res.numel() * 2 if res is not None else 0) + w_bytes

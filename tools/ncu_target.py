@@ -33,7 +33,7 @@ def main():
         g = torch.Generator(device="cuda").manual_seed(0)
         for i in ids:
             L = eng.plan.layers[i]
-            if L.kind == 1:
+            if L.kind in (1, 3):
                 x = torch.zeros(n, 224, 232, 4, device="cuda", dtype=torch.bfloat16)
                 x[:, :, 4:228, :3] = torch.randn(n, 224, 224, 3, device="cuda", generator=g).to(torch.bfloat16)
             else:
