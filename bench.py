@@ -3,7 +3,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Workload (BASELINE.json configs[1]): one synthetic H36M-shaped sequence of 2000 uint8 frames 224x224x3, batch 256.
-A step = one pass of the hot path (K1 preprocess -> stem -> 52 bottleneck convs -> fused avg-pool) over one batch of
+A step = one pass of the hot path (K1 preprocess -> fused stem+maxpool -> 52 bottleneck convs, the last with the
+average pool fused) over one batch of
 256 frames taken cyclically from the sequence.  The sequence (301 MB) is resident in HBM and larger than the 126 MB
 L2, and consecutive steps read different batches, so inputs come from HBM every step.
 
@@ -11,7 +12,7 @@ One JSON line on stdout (rank 0):
   value      frames/s over all ranks, inputs already resident in HBM, CUDA-event timed, max over ranks
   e2e        the same metric through the public host-buffer API (phdfx.StreamingExtractor): pinned host uint8 frames
              -> H2D -> features -> D2H, copies inside the timed region
-  roofline   trunk (53 conv launches + maxpool per step) FLOP/s vs the measured dense-bf16 peak; 2*MAC convention:
+  roofline   trunk (stem+maxpool launch + 52 conv launches per step) FLOP/s vs the measured dense-bf16 peak; 2*MAC convention:
              8.174 GFLOP per frame (4 087 136 256 MAC)
   cpu_baseline  the reference's CPU path (torchvision ResNet-50 fp32 eager, exactly src/preprocess_resnet_features.py
              :207-209 + the reference-equivalent crop/resize/normalise) on this box's host cores, bounded sample
@@ -216,8 +217,14 @@ def run_b200(args):
         b = i % n_batches
         eng.extract_u8(seq[b * BATCH:(b + 1) * BATCH], None, out=out)
 
+    def gather_all():
+        if world > 1:
+            dst = torch.empty(world * K * BATCH, 2048, dtype=torch.float32, device=dev) if rank == 0 else None
+            dist.gather(feats_all.view(-1, 2048), list(dst.chunk(world)) if rank == 0 else None, dst=0)
+
     for i in range(Wm):
         step(i, scratch)
+    gather_all()  # warm-up: NCCL sets up its peer connections lazily on the first point-to-point operation
     barrier()
 
     # ---- device-resident throughput (value) ----------------------------------------------------------------
@@ -229,9 +236,7 @@ def run_b200(args):
         for i in range(K):
             step(Wm + i, feats_all[i])
             launches += eng.launches
-        if world > 1:
-            gathered = torch.empty(world * K * BATCH, 2048, dtype=torch.float32, device=dev) if rank == 0 else None
-            dist.gather(feats_all.view(-1, 2048), list(gathered.chunk(world)) if rank == 0 else None, dst=0)
+        gather_all()  # the only collective of the path: final feature gather to rank 0 over NVLink
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -260,9 +265,13 @@ def run_b200(args):
     achieved_tf = BATCH * FLOP_PER_FRAME / (trunk_ms / 1e3) / 1e12
 
     # ---- K1 alone (HBM-bound) ----------------------------------------------------------------------------------
+    k1_out = x4s[0]
+    for i in range(2):
+        eng.preprocess_u8(seq[i * BATCH:(i + 1) * BATCH], None, out=k1_out)
+    torch.cuda.synchronize(dev)
     e0.record()
     for i in range(reps):
-        eng.preprocess_u8(seq[(i % n_batches) * BATCH:(i % n_batches + 1) * BATCH], None)
+        eng.preprocess_u8(seq[(i % n_batches) * BATCH:(i % n_batches + 1) * BATCH], None, out=k1_out)
     e1.record()
     torch.cuda.synchronize(dev)
     k1_ms = e0.elapsed_time(e1) / reps
@@ -316,7 +325,7 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved_tf / pk["bf16_sustained"], "traffic": None,
-                         "kernel": "conv_igemm_kernel: 53 launches (stem + 52 bottleneck convs) + 1 maxpool per step",
+                         "kernel": "trunk = stem_pool_kernel (1 launch) + conv_igemm_kernel (52 launches) per step",
                          "trunk_ms_per_step": trunk_ms, "flop_per_frame": FLOP_PER_FRAME,
                          "frac_of_burst_peak": achieved_tf / pk["bf16_burst"], "peak_burst": pk["bf16_burst"],
                          "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"},

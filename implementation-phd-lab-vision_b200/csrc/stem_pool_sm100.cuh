@@ -9,7 +9,7 @@
 // window starting 16*q bytes into the row, i.e. a K-major no-swizzle operand whose rows OVERLAP (row stride 16 B,
 // K-chunk stride LBO = 16 B, 8-row-group stride SBO = 128 B) — the tensor core does the sliding window.  Rows outside
 // the image read a zeroed slot.  K = 7 filter rows x 32 (8 px x 4 ch; tap -1 and channel 3 carry zero weights).
-//   warp 0    producer: cp.async.bulk of input row PAIRS into an 8-slot ring (2 x 1856 B per slot)
+//   warp 0    producer: cp.async.bulk of input row PAIRS into a 16-slot ring (2 x 1856 B per slot)
 //   warp 1    MMA issuer: 14 tcgen05.mma (M=128, N=64, K=16) per conv row, weights resident in smem (28 KB);
 //             a step's even/odd conv rows go to adjacent 64-column halves of one of two TMEM buffers
 //   warp 2    DMA: TMA store of pooled rows (56 px x 64 ch = 7 KB each); owns the TMEM allocation
@@ -25,7 +25,7 @@ namespace phdfxk {
 constexpr int kSpIn = 224, kSpInPitchPx = 232, kSpOut = 112, kSpPool = 56;
 constexpr int kSpRowBytes = kSpInPitchPx * 8;   // 1856
 constexpr int kSpRowPitch = 2048;               // smem pitch of one input row
-constexpr int kSpPairSlots = 8;                 // ring of row pairs
+constexpr int kSpPairSlots = 16;                // ring of row pairs (2 steps x 2 rows in flight need 7; the rest is prefetch)
 constexpr int kSpBand = 16;                     // conv rows per work item
 constexpr int kSpBandsPerFrame = kSpOut / kSpBand;  // 7
 constexpr int kSpConvRowBytes = kSpOut * 128;   // 14336: one conv row, 112 px x 64 ch bf16
@@ -91,7 +91,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = StemPoolSmem;
-  uint64_t* pair_full = reinterpret_cast<uint64_t*>(smem + L::BARS);  // [8]
+  uint64_t* pair_full = reinterpret_cast<uint64_t*>(smem + L::BARS);  // [kSpPairSlots]
   uint64_t* pair_empty = pair_full + kSpPairSlots;                   // [8]
   uint64_t* tmem_full = pair_empty + kSpPairSlots;                   // [2]
   uint64_t* tmem_empty = tmem_full + 2;                              // [2]

@@ -131,11 +131,16 @@ class B200Backbone:
 
     @torch.no_grad()
     def preprocess_u8(self, frames: torch.Tensor, boxes: Optional[torch.Tensor] = None,
-                      flip_w: bool = False) -> torch.Tensor:
+                      flip_w: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """K1 alone: uint8 [N,H,W,3] -> bf16 NHWC4p [N,224,232,4] (the trunk's input layout)."""
         self._check_dev(frames, "frames")
         n, H, W, _ = frames.shape
-        out = torch.empty(n, _lib.IMG, _lib.IN_WPAD, _lib.IN_CPAD, device=self.device, dtype=torch.bfloat16)
+        if out is None:
+            out = torch.empty(n, _lib.IMG, _lib.IN_WPAD, _lib.IN_CPAD, device=self.device, dtype=torch.bfloat16)
+        elif out.dtype != torch.bfloat16 or tuple(out.shape) != (n, _lib.IMG, _lib.IN_WPAD, _lib.IN_CPAD):
+            raise RuntimeError("out must be bf16 [N,224,232,4]")
+        else:
+            self._check_dev(out, "out")
         with torch.cuda.device(self.device):
             for i in range(0, n, self.max_frames):
                 m = min(self.max_frames, n - i)
