@@ -100,6 +100,23 @@ int encode_tiled(phdfx_t* h, CUtensorMap* m, const void* base, int rank, const c
   return 0;
 }
 
+// ---- launch with programmatic stream serialisation (PDL): the kernel may start while its predecessor drains; every
+// kernel of this library executes griddepcontrol.wait before it touches activations.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- per-layer geometry ---------------------------------------------------------------------------------------
 struct Geo {
   int P, Q;        // output spatial
@@ -255,8 +272,8 @@ int launch_conv_t(phdfx_t* h, const LayerMaps& maps, const ConvParams& p, cudaSt
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  conv_igemm_kernel<BN, MODE><<<grid, kNumThreads, Cfg::SMEM_BYTES, st>>>(maps.a, maps.b, maps.o, maps.r, p);
-  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, launch_pdl(conv_igemm_kernel<BN, MODE>, dim3(grid), dim3(kNumThreads), Cfg::SMEM_BYTES, st, maps.a,
+                         maps.b, maps.o, maps.r, p));
   h->last_launches++;
   return 0;
 }
@@ -326,8 +343,7 @@ int launch_stem_pool(phdfx_t* h, const phdfx_layer_desc& L, const CUtensorMap& m
   p.n_frames = n;
   const int bands = n * kSpBandsPerFrame;
   const int grid = bands < h->num_sms ? bands : h->num_sms;
-  stem_pool_kernel<<<grid, kSpThreads, smem, st>>>(map_out, p);
-  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, launch_pdl(stem_pool_kernel, dim3(grid), dim3(kSpThreads), smem, st, map_out, p));
   h->last_launches++;
   return 0;
 }
@@ -338,10 +354,9 @@ int launch_maxpool(phdfx_t* h, const phdfx_layer_desc& L, const void* in, void* 
   long long blocks = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(h->num_sms) * 16;
   if (blocks > cap) blocks = cap;
-  maxpool3x3s2_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(static_cast<const __nv_bfloat16*>(in), n, L.hin,
-                                                                    L.win, L.cin,
-                                                                    static_cast<__nv_bfloat16*>(out));
-  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, launch_pdl(maxpool3x3s2_kernel, dim3(static_cast<int>(blocks)), dim3(threads), 0, st,
+                         static_cast<const __nv_bfloat16*>(in), n, static_cast<int>(L.hin),
+                         static_cast<int>(L.win), static_cast<int>(L.cin), static_cast<__nv_bfloat16*>(out)));
   h->last_launches++;
   return 0;
 }
@@ -494,10 +509,17 @@ int phdfx_preprocess_u8(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W
   CUDA_TRY(h, cudaSetDevice(h->device));
   h->last_launches = 0;
   void* out = d_out ? d_out : h->bufs[0];
-  const long long total = static_cast<long long>(n) * kImg * kStemWPad;
-  preprocess_u8_kernel<<<grid_1d(h, total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_frames, n, H, W, d_boxes, flip_w, static_cast<__nv_bfloat16*>(out));
-  CUDA_TRY(h, cudaGetLastError());
+  const size_t k1_row_cap = (static_cast<size_t>(W) * 3 + 32 + 15) & ~static_cast<size_t>(15);
+  const size_t k1_smem = kK1Warps * 2 * k1_row_cap;
+  if (k1_smem > 200 * 1024) return fail(h, PHDFX_ERR_INVALID, "frame width %d too large for the preprocess kernel", W);
+  if (k1_smem > 48 * 1024)
+    CUDA_TRY(h, cudaFuncSetAttribute(preprocess_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(k1_smem)));
+  const int k1_blocks = (n * kImg + kK1Warps - 1) / kK1Warps;
+  const int k1_cap = h->num_sms * 16;
+  CUDA_TRY(h, launch_pdl(preprocess_u8_kernel, dim3(k1_blocks < k1_cap ? k1_blocks : k1_cap), dim3(kK1Warps * 32),
+                         k1_smem, static_cast<cudaStream_t>(stream), d_frames, n, H, W, d_boxes, flip_w,
+                         static_cast<__nv_bfloat16*>(out)));
   h->last_launches++;
   return 0;
 }
@@ -509,9 +531,8 @@ int phdfx_nchw_f32_to_nhwc_bf16(phdfx_t* h, const float* d_x, int n, void* d_out
   h->last_launches = 0;
   void* out = d_out ? d_out : h->bufs[0];
   const long long total = static_cast<long long>(n) * kImg * kStemWPad;
-  nchw_f32_to_stem_kernel<<<grid_1d(h, total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_x, n, static_cast<__nv_bfloat16*>(out));
-  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, launch_pdl(nchw_f32_to_stem_kernel, dim3(grid_1d(h, total, 256)), dim3(256), 0,
+                         static_cast<cudaStream_t>(stream), d_x, n, static_cast<__nv_bfloat16*>(out)));
   h->last_launches++;
   return 0;
 }

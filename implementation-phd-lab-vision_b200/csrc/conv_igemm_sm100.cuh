@@ -141,6 +141,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's
+  // tail; nothing below touches activations before the previous grid has completed.
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer

@@ -8,6 +8,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "ptx_sm100.cuh"
+
 namespace phdfxk {
 
 constexpr int kImg = 224;        // network input side
@@ -22,74 +24,113 @@ constexpr int kStemLeftPad = 4;
 // DataLoader workers run (1 thread -> channels-last kernel; pinned bit-for-bit by oracle/preprocess_ref.py):
 //   src = max(0, fma(scale, dst+0.5, -0.5)), scale = in/out;  wij = lam_h_i * lam_w_j;
 //   value = fma(w11,v11, fma(w10,v10, fma(w00,v00, w01*v01))).
-__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
-                                     const int32_t* __restrict__ boxes, int flip_w, __nv_bfloat16* __restrict__ out) {
-  const int total = n_frames * kImg * kStemWPad;
+// One WARP per (frame, output row): both source rows of the bilinear stencil are the same for the whole output row, so
+// the warp stages them in its own slice of shared memory with coalesced 16-byte loads (no block-wide barrier) and
+// every lane then produces 8 of the row's 232 output pixels from there.
+// Dynamic shared memory: kK1Warps * 2 * row_cap bytes, row_cap = round_up(3*W + 32, 16).
+constexpr int kK1Warps = 8;
+
+__global__ void __launch_bounds__(kK1Warps * 32)
+preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
+                     const int32_t* __restrict__ boxes, int flip_w, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t s_rows[];
+  griddep_launch_dependents();
+  griddep_wait();  // the arena input buffer may still be read by the previous step's stem kernel
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int wp = idx % kStemWPad;
-    const int y = (idx / kStemWPad) % kImg;
-    const int n = idx / (kStemWPad * kImg);
-    uint2 o = make_uint2(0u, 0u);
-    int x = wp - kStemLeftPad;
-    if (x >= 0 && x < kImg) {
-      if (flip_w) x = kImg - 1 - x;
-      int top = 0, left = 0, bh = H, bw = W;
-      if (boxes != nullptr) {
-        top = boxes[4 * n + 0];
-        left = boxes[4 * n + 1];
-        bh = boxes[4 * n + 2];
-        bw = boxes[4 * n + 3];
-      }
-      const float scale_h = __fdiv_rn(static_cast<float>(bh), static_cast<float>(kImg));
-      const float scale_w = __fdiv_rn(static_cast<float>(bw), static_cast<float>(kImg));
-      float sy = __fmaf_rn(scale_h, static_cast<float>(y) + 0.5f, -0.5f);
-      float sx = __fmaf_rn(scale_w, static_cast<float>(x) + 0.5f, -0.5f);
-      sy = sy < 0.0f ? 0.0f : sy;
-      sx = sx < 0.0f ? 0.0f : sx;
-      int y0 = static_cast<int>(sy);
-      int x0 = static_cast<int>(sx);
-      y0 = y0 > bh - 1 ? bh - 1 : y0;
-      x0 = x0 > bw - 1 ? bw - 1 : x0;
-      const int y1 = y0 + (y0 < bh - 1 ? 1 : 0);
-      const int x1 = x0 + (x0 < bw - 1 ? 1 : 0);
-      float ly1 = __fsub_rn(sy, static_cast<float>(y0));
-      float lx1 = __fsub_rn(sx, static_cast<float>(x0));
-      ly1 = fminf(fmaxf(ly1, 0.0f), 1.0f);
-      lx1 = fminf(fmaxf(lx1, 0.0f), 1.0f);
-      const float ly0 = __fsub_rn(1.0f, ly1);
-      const float lx0 = __fsub_rn(1.0f, lx1);
-      const uint8_t* base = frames + static_cast<size_t>(n) * H * W * 3;
-      const uint8_t* p00 = base + (static_cast<size_t>(top + y0) * W + (left + x0)) * 3;
-      const uint8_t* p01 = base + (static_cast<size_t>(top + y0) * W + (left + x1)) * 3;
-      const uint8_t* p10 = base + (static_cast<size_t>(top + y1) * W + (left + x0)) * 3;
-      const uint8_t* p11 = base + (static_cast<size_t>(top + y1) * W + (left + x1)) * 3;
-      const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1);
-      const float w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
-      float r[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v00 = static_cast<float>(__ldg(p00 + c));
-        const float v01 = static_cast<float>(__ldg(p01 + c));
-        const float v10 = static_cast<float>(__ldg(p10 + c));
-        const float v11 = static_cast<float>(__ldg(p11 + c));
-        const float v = __fmaf_rn(w11, v11, __fmaf_rn(w10, v10, __fmaf_rn(w00, v00, __fmul_rn(w01, v01))));
-        const float u8 = fminf(fmaxf(rintf(v), 0.0f), 255.0f);  // round half to even, uint8 range
-        const float x01 = __fdiv_rn(u8, 255.0f);
-        r[c] = __fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]);
-      }
-      const __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]);
-      const __nv_bfloat162 b = __floats2bfloat162_rn(r[2], 0.0f);
-      o.x = *reinterpret_cast<const uint32_t*>(&a);
-      o.y = *reinterpret_cast<const uint32_t*>(&b);
+  const int row_cap = (3 * W + 32 + 15) & ~15;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* s0 = s_rows + static_cast<size_t>(warp) * 2 * row_cap;
+  uint8_t* s1 = s0 + row_cap;
+  const uint8_t* buf_begin = frames;
+  const uint8_t* buf_end = frames + static_cast<size_t>(n_frames) * H * W * 3;
+  const int total_rows = n_frames * kImg;
+  for (int rowi = blockIdx.x * kK1Warps + warp; rowi < total_rows; rowi += gridDim.x * kK1Warps) {
+    const int n = rowi / kImg;
+    const int y = rowi - n * kImg;
+    int top = 0, left = 0, bh = H, bw = W;
+    if (boxes != nullptr) {
+      top = boxes[4 * n + 0];
+      left = boxes[4 * n + 1];
+      bh = boxes[4 * n + 2];
+      bw = boxes[4 * n + 3];
     }
-    reinterpret_cast<uint2*>(out)[idx] = o;
+    const float scale_h = __fdiv_rn(static_cast<float>(bh), static_cast<float>(kImg));
+    float sy = __fmaf_rn(scale_h, static_cast<float>(y) + 0.5f, -0.5f);
+    sy = sy < 0.0f ? 0.0f : sy;
+    int y0 = static_cast<int>(sy);
+    y0 = y0 > bh - 1 ? bh - 1 : y0;
+    const int y1 = y0 + (y0 < bh - 1 ? 1 : 0);
+    float ly1 = __fsub_rn(sy, static_cast<float>(y0));
+    ly1 = fminf(fmaxf(ly1, 0.0f), 1.0f);
+    const float ly0 = __fsub_rn(1.0f, ly1);
+    // stage rows y0 (and y1 when it carries weight) of the crop: bytes [left*3, (left+bw)*3) of the frame row
+    const uint8_t* base = frames + static_cast<size_t>(n) * H * W * 3;
+    const uint8_t* r0 = base + (static_cast<size_t>(top + y0) * W + left) * 3;
+    const uint8_t* r1 = base + (static_cast<size_t>(top + y1) * W + left) * 3;
+    const int off0 = static_cast<int>(reinterpret_cast<uintptr_t>(r0) & 15);
+    const int off1 = static_cast<int>(reinterpret_cast<uintptr_t>(r1) & 15);
+    const bool need1 = ly1 != 0.0f;  // weight-0 taps add exactly +0: skip the second row (identity-size crops)
+    __syncwarp();                    // the previous row's readers are done with s0 / s1
+    for (int pass = 0; pass < (need1 ? 2 : 1); ++pass) {
+      const uint8_t* src = (pass == 0 ? r0 - off0 : r1 - off1);  // 16-byte aligned
+      uint8_t* dst = pass == 0 ? s0 : s1;
+      const int nvec = ((pass == 0 ? off0 : off1) + bw * 3 + 15) >> 4;
+      for (int i = lane; i < nvec; i += 32) {
+        const uint8_t* g = src + 16 * i;
+        if (g >= buf_begin && g + 16 <= buf_end) {
+          reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(g));
+        } else {  // first / last vector of the whole buffer: stay inside it
+          for (int k = 0; k < 16; ++k) dst[16 * i + k] = (g + k >= buf_begin && g + k < buf_end) ? g[k] : 0;
+        }
+      }
+    }
+    __syncwarp();
+    const uint8_t* t0 = s0 + off0;
+    const uint8_t* t1 = need1 ? s1 + off1 : t0;
+    const float scale_w = __fdiv_rn(static_cast<float>(bw), static_cast<float>(kImg));
+    for (int wp = lane; wp < kStemWPad; wp += 32) {
+      uint2 o = make_uint2(0u, 0u);
+      int x = wp - kStemLeftPad;
+      if (x >= 0 && x < kImg) {
+        if (flip_w) x = kImg - 1 - x;
+        float sx = __fmaf_rn(scale_w, static_cast<float>(x) + 0.5f, -0.5f);
+        sx = sx < 0.0f ? 0.0f : sx;
+        int x0 = static_cast<int>(sx);
+        x0 = x0 > bw - 1 ? bw - 1 : x0;
+        const int x1 = x0 + (x0 < bw - 1 ? 1 : 0);
+        float lx1 = __fsub_rn(sx, static_cast<float>(x0));
+        lx1 = fminf(fmaxf(lx1, 0.0f), 1.0f);
+        const float lx0 = __fsub_rn(1.0f, lx1);
+        const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1);
+        const float w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
+        float r[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v00 = static_cast<float>(t0[x0 * 3 + c]);
+          const float v01 = static_cast<float>(t0[x1 * 3 + c]);
+          const float v10 = static_cast<float>(t1[x0 * 3 + c]);
+          const float v11 = static_cast<float>(t1[x1 * 3 + c]);
+          const float v = __fmaf_rn(w11, v11, __fmaf_rn(w10, v10, __fmaf_rn(w00, v00, __fmul_rn(w01, v01))));
+          const float u8 = fminf(fmaxf(rintf(v), 0.0f), 255.0f);  // round half to even, uint8 range
+          const float x01 = __fdiv_rn(u8, 255.0f);
+          r[c] = __fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]);
+        }
+        const __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]);
+        const __nv_bfloat162 bq = __floats2bfloat162_rn(r[2], 0.0f);
+        o.x = *reinterpret_cast<const uint32_t*>(&a);
+        o.y = *reinterpret_cast<const uint32_t*>(&bq);
+      }
+      reinterpret_cast<uint2*>(out)[static_cast<size_t>(rowi) * kStemWPad + wp] = o;
+    }
   }
 }
 
 // Seam A repack: already-normalised fp32 NCHW [N,3,224,224] (src/preprocess_resnet_features.py:295) -> NHWC4p.
 __global__ void nchw_f32_to_stem_kernel(const float* __restrict__ x, int n_frames, __nv_bfloat16* __restrict__ out) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int total = n_frames * kImg * kStemWPad;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int wp = idx % kStemWPad;
@@ -112,6 +153,8 @@ __global__ void nchw_f32_to_stem_kernel(const float* __restrict__ x, int n_frame
 // MaxPool2d(3, stride 2, pad 1) over NHWC bf16 (torchvision models/resnet.py:200); 8 channels per thread.
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, int n_frames, int Hin, int Win, int C,
                                     __nv_bfloat16* __restrict__ out) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int Ho = (Hin + 2 - 3) / 2 + 1;
   const int Wo = (Win + 2 - 3) / 2 + 1;
   const int cg = C / 8;

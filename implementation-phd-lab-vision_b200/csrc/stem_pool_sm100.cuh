@@ -133,6 +133,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_launch_dependents();  // PDL: see conv_igemm_sm100.cuh
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (whole warp, uniform flow)
