@@ -510,7 +510,7 @@ int phdfx_preprocess_u8(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W
   h->last_launches = 0;
   void* out = d_out ? d_out : h->bufs[0];
   const size_t k1_row_cap = (static_cast<size_t>(W) * 3 + 32 + 15) & ~static_cast<size_t>(15);
-  const size_t k1_smem = kK1Warps * 2 * k1_row_cap;
+  const size_t k1_smem = kK1LutBytes + kK1Warps * 2 * k1_row_cap;
   if (k1_smem > 200 * 1024) return fail(h, PHDFX_ERR_INVALID, "frame width %d too large for the preprocess kernel", W);
   if (k1_smem > 48 * 1024)
     CUDA_TRY(h, cudaFuncSetAttribute(preprocess_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -27,8 +27,11 @@ constexpr int kStemLeftPad = 4;
 // One WARP per (frame, output row): both source rows of the bilinear stencil are the same for the whole output row, so
 // the warp stages them in its own slice of shared memory with coalesced 16-byte loads (no block-wide barrier) and
 // every lane then produces 8 of the row's 232 output pixels from there.
-// Dynamic shared memory: kK1Warps * 2 * row_cap bytes, row_cap = round_up(3*W + 32, 16).
+// The /255 and (x - mean)/std steps depend only on (channel, uint8 value): each block builds the 3 x 256 table of
+// final bf16 values once, with exactly the reference's fp32 operations, and pixels look their result up.
+// Dynamic shared memory: 1536 (table) + kK1Warps * 2 * row_cap bytes, row_cap = round_up(3*W + 32, 16).
 constexpr int kK1Warps = 8;
+constexpr int kK1LutBytes = 3 * 256 * 2;
 
 __global__ void __launch_bounds__(kK1Warps * 32)
 preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
@@ -41,7 +44,14 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
   const int row_cap = (3 * W + 32 + 15) & ~15;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  uint8_t* s0 = s_rows + static_cast<size_t>(warp) * 2 * row_cap;
+  __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(s_rows);  // [3][256]
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+    const int c = i >> 8;
+    const float x01 = __fdiv_rn(static_cast<float>(i & 255), 255.0f);             // frames.to(float32) / 255.0
+    lut[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]));    // Normalize, then bf16
+  }
+  __syncthreads();
+  uint8_t* s0 = s_rows + kK1LutBytes + static_cast<size_t>(warp) * 2 * row_cap;
   uint8_t* s1 = s0 + row_cap;
   const uint8_t* buf_begin = frames;
   const uint8_t* buf_end = frames + static_cast<size_t>(n_frames) * H * W * 3;
@@ -105,7 +115,7 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
         const float lx0 = __fsub_rn(1.0f, lx1);
         const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1);
         const float w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
-        float r[3];
+        uint32_t r[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float v00 = static_cast<float>(t0[x0 * 3 + c]);
@@ -113,14 +123,11 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
           const float v10 = static_cast<float>(t1[x0 * 3 + c]);
           const float v11 = static_cast<float>(t1[x1 * 3 + c]);
           const float v = __fmaf_rn(w11, v11, __fmaf_rn(w10, v10, __fmaf_rn(w00, v00, __fmul_rn(w01, v01))));
-          const float u8 = fminf(fmaxf(rintf(v), 0.0f), 255.0f);  // round half to even, uint8 range
-          const float x01 = __fdiv_rn(u8, 255.0f);
-          r[c] = __fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]);
+          const int u8 = static_cast<int>(fminf(fmaxf(rintf(v), 0.0f), 255.0f));  // round half to even, uint8 range
+          r[c] = reinterpret_cast<const uint16_t*>(lut)[c * 256 + u8];
         }
-        const __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]);
-        const __nv_bfloat162 bq = __floats2bfloat162_rn(r[2], 0.0f);
-        o.x = *reinterpret_cast<const uint32_t*>(&a);
-        o.y = *reinterpret_cast<const uint32_t*>(&bq);
+        o.x = r[0] | (r[1] << 16);
+        o.y = r[2];
       }
       reinterpret_cast<uint2*>(out)[static_cast<size_t>(rowi) * kStemWPad + wp] = o;
     }

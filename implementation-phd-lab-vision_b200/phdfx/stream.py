@@ -17,7 +17,7 @@ from .backbone import B200Backbone
 class StreamingExtractor:
     """features = StreamingExtractor(engine)(frames_host_u8 [N,H,W,3], boxes_host [N,4] | None) -> host fp32 [N,2048]"""
 
-    def __init__(self, engine: B200Backbone, batch: int = 256, save_fp16: bool = False):
+    def __init__(self, engine: B200Backbone, batch: int = 256, save_fp16: bool = False, use_graphs: bool = True):
         if batch > engine.max_frames:
             raise RuntimeError(f"batch {batch} > engine.max_frames {engine.max_frames}")
         self.eng = engine
@@ -27,6 +27,8 @@ class StreamingExtractor:
         self.copy_in = torch.cuda.Stream(self.dev)
         self.compute = torch.cuda.Stream(self.dev)
         self.copy_out = torch.cuda.Stream(self.dev)
+        self.use_graphs = use_graphs
+        self._graphs = {}  # (slot, with_boxes, flip_w) -> ExtractGraph over the slot's fixed device buffers
         self._shape = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -36,6 +38,7 @@ class StreamingExtractor:
         if self._shape == (H, W):
             return
         self._shape = (H, W)
+        self._graphs = {}
         self.d_frames = [torch.empty(self.batch, H, W, 3, dtype=torch.uint8, device=self.dev) for _ in range(2)]
         self.d_boxes = [torch.empty(self.batch, 4, dtype=torch.int32, device=self.dev) for _ in range(2)]
         self.d_feats = [torch.empty(self.batch, self.eng.FEAT_DIM, dtype=torch.float32, device=self.dev)
@@ -83,9 +86,20 @@ class StreamingExtractor:
                 self.compute.wait_event(self.ev_in[slot])
                 if i >= 2:
                     self.compute.wait_event(self.ev_out[slot])  # slot's previous result has been downloaded
-                self.eng.extract_u8(self.d_frames[slot][:m], self.d_boxes[slot][:m] if boxes is not None else None,
-                                    flip_w=flip_w, out=self.d_feats[slot][:m])
-                self.launches += self.eng.launches
+                if self.use_graphs and m == self.batch:
+                    key = (slot, boxes is not None, bool(flip_w))
+                    g = self._graphs.get(key)
+                    if g is None:  # first full batch on this slot: capture (the capture run does the work too)
+                        g = self.eng.capture_extract(self.d_frames[slot], self.d_boxes[slot] if boxes is not None
+                                                     else None, flip_w=flip_w, out=self.d_feats[slot])
+                        self._graphs[key] = g
+                    g.replay()
+                    self.launches += g.launches
+                else:
+                    self.eng.extract_u8(self.d_frames[slot][:m],
+                                        self.d_boxes[slot][:m] if boxes is not None else None, flip_w=flip_w,
+                                        out=self.d_feats[slot][:m])
+                    self.launches += self.eng.launches
                 if self.out_dtype != torch.float32:
                     self.d_out[slot][:m].copy_(self.d_feats[slot][:m])
                 self.ev_done[slot].record(self.compute)

@@ -295,6 +295,19 @@ def test_streaming_host_api(eng):
     assert torch.equal(se16(torch.from_numpy(frames)), dev.to(torch.float16))
 
 
+def test_cuda_graph_replay_is_bit_identical(eng):
+    """One whole step captured into a CUDA graph (programmatic-dependent-launch edges included): refill the input
+    buffers in place, replay, same bits as the eager call."""
+    frames = torch.from_numpy(R.seeded_frames(20, 240, 250, 14)).cuda()
+    boxes = torch.tensor([(3, 4, 230, 230)] * 20, dtype=torch.int32, device="cuda")
+    buf = frames[:10].clone()
+    g = eng.capture_extract(buf, boxes[:10].clone())
+    assert torch.equal(g.replay(), eng.extract_u8(frames[:10].contiguous(), boxes[:10].contiguous()))
+    buf.copy_(frames[10:])
+    assert torch.equal(g.replay(), eng.extract_u8(frames[10:].contiguous(), boxes[10:].contiguous()))
+    assert g.launches == 54
+
+
 def test_errors_are_loud(eng):
     with pytest.raises(RuntimeError):
         eng(torch.zeros(2, 3, 200, 200, device="cuda"))
