@@ -124,7 +124,10 @@ struct Geo {
   int bn;          // tile N
   int K;           // GEMM K (packed)
   int num_kb;
+  int halo_rt;     // MODE_HALO: output rows per tile
 };
+
+bool g_use_halo = true;  // PHDFX_NO_HALO=1 (read at phdfx_create) falls back to the im2col path for A/B measurements
 
 Geo geometry(const phdfx_layer_desc& L) {
   Geo g{};
@@ -142,7 +145,11 @@ Geo geometry(const phdfx_layer_desc& L) {
       g.mode = MODE_GAP;
     else if (L.r == 1 && L.s == 1 && L.stride == 1 && L.pad == 0)
       g.mode = MODE_TILED;
-    else
+    else if (g_use_halo && L.r == 3 && L.s == 3 && L.stride == 1 && L.pad == 1 && L.hin == L.win &&
+             ((L.hin == 56 && L.cin == 64 && L.cout == 64) || (L.hin == 28 && L.cin == 128 && L.cout == 128))) {
+      g.mode = MODE_HALO;
+      g.halo_rt = L.hin == 56 ? 2 : 4;  // 2*(56+2) = 116, 4*(28+2) = 120 padded-raster rows <= 128
+    } else
       g.mode = MODE_IM2COL;
     g.bn = L.cout >= 256 ? 256 : L.cout;
   }
@@ -198,7 +205,13 @@ int build_maps(phdfx_t* h, const phdfx_layer_desc& L, const void* in, const void
     cuuint64_t od[2] = {cout, rows};
     cuuint64_t os[1] = {cout * 2};
     cuuint32_t ob[2] = {kGroupCols, kBlockM};
-    if (g.mode == MODE_STEM) {
+    if (g.mode == MODE_HALO) {
+      cuuint64_t d4[4] = {cout, static_cast<cuuint64_t>(g.Q), static_cast<cuuint64_t>(g.P),
+                          static_cast<cuuint64_t>(frames)};
+      cuuint64_t s4[3] = {cout * 2, cout * 2 * g.Q, cout * 2 * g.Q * g.P};
+      cuuint32_t b4[4] = {kGroupCols, static_cast<cuuint32_t>(g.Q), static_cast<cuuint32_t>(g.halo_rt), 1};
+      if (int rc = encode_tiled(h, &out->o, outp, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_128B, "halo out")) return rc;
+    } else if (g.mode == MODE_STEM) {
       cuuint64_t d4[4] = {64, kStemOut, kStemOut, static_cast<cuuint64_t>(frames)};
       cuuint64_t s4[3] = {128, 128ull * kStemOut, 128ull * kStemOut * kStemOut};
       cuuint32_t b4[4] = {64, kStemTileQ, kStemTileP, 1};
@@ -230,6 +243,12 @@ int build_maps(phdfx_t* h, const phdfx_layer_desc& L, const void* in, const void
     cuuint64_t str[1] = {cin * 2};
     cuuint32_t box[2] = {64, kBlockM};
     if (int rc = encode_tiled(h, &out->a, in, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "tiled A")) return rc;
+  } else if (g.mode == MODE_HALO) {
+    cuuint64_t dims[4] = {cin, static_cast<cuuint64_t>(L.win), static_cast<cuuint64_t>(L.hin),
+                          static_cast<cuuint64_t>(frames)};
+    cuuint64_t str[3] = {cin * 2, cin * 2 * L.win, cin * 2 * L.win * L.hin};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(L.win + 2), static_cast<cuuint32_t>(g.halo_rt + 2), 1};
+    if (int rc = encode_tiled(h, &out->a, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "halo A")) return rc;
   } else if (g.mode == MODE_GAP) {
     cuuint64_t dims[3] = {cin, kGapRowsPerFrame, static_cast<cuuint64_t>(frames)};
     cuuint64_t str[2] = {cin * 2, cin * 2 * kGapRowsPerFrame};
@@ -297,7 +316,10 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bo
   p.feats = L.gap ? static_cast<float*>(out) : nullptr;
   p.M = n * g.P * g.Q;
   p.n_tiles = L.cout / g.bn;
-  if (g.mode == MODE_STEM)
+  p.halo_rt = g.halo_rt;
+  if (g.mode == MODE_HALO)
+    p.m_tiles = n * (g.P / g.halo_rt);
+  else if (g.mode == MODE_STEM)
     p.m_tiles = n * kStemTilesPerFrame;
   else if (g.mode == MODE_GAP)
     p.m_tiles = (n + 1) / 2;
@@ -309,6 +331,9 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bo
       return launch_conv_t<64, MODE_STEM>(h, maps, p, st);
     case MODE_GAP:
       return launch_conv_t<256, MODE_GAP>(h, maps, p, st);
+    case MODE_HALO:
+      if (g.bn == 64) return launch_conv_t<64, MODE_HALO>(h, maps, p, st);
+      return launch_conv_t<128, MODE_HALO>(h, maps, p, st);
     case MODE_TILED:
       if (g.bn == 64) return launch_conv_t<64, MODE_TILED>(h, maps, p, st);
       if (g.bn == 128) return launch_conv_t<128, MODE_TILED>(h, maps, p, st);
@@ -399,6 +424,7 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   if (!out) return fail(nullptr, PHDFX_ERR_INVALID, "null out pointer");
   *out = nullptr;
   if (max_frames < 1) return fail(nullptr, PHDFX_ERR_INVALID, "max_frames must be >= 1");
+  if (const char* e = getenv("PHDFX_NO_HALO")) g_use_halo = !(e[0] == '1');
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)

@@ -31,6 +31,11 @@ enum ConvMode : int {
   MODE_IM2COL = 1,  // 3x3 (any stride) and strided 1x1: TMA im2col mode over NHWC
   MODE_STEM = 2,    // 7x7/2 stem: per filter row an 8-pixel x 4-channel window, overlapping-stride 5-D map
   MODE_GAP = 3,     // last 1x1 conv: tile = 2 whole frames (98 rows), epilogue emits the 7x7 mean in fp32
+  MODE_HALO = 4,    // 3x3 stride 1 pad 1 on 56x56 (BN=64) / 28x28 (BN=128): the tile is R_t output rows of one frame
+                    // in "padded raster" order (row pitch W+2); ONE zero-padded input patch per 64-channel block is
+                    // loaded (tiled 4-D TMA, OOB zero fill = the halo) and all nine taps read it through
+                    // row-shifted 128B-swizzled descriptors (start = patch + (r*(W+2)+s)*128 B) — 9x less A traffic
+                    // than the im2col path; only the weights stream through the stage ring
 };
 
 struct ConvParams {
@@ -45,6 +50,7 @@ struct ConvParams {
   int relu;
   int has_res;     // residual tile is TMA-loaded through mapR
   int n_frames;
+  int halo_rt;     // MODE_HALO: output rows per tile (2 for 56x56, 4 for 28x28)
   const float* bias;  // [Cout] folded BN bias
   float* feats;       // MODE_GAP: [n_frames, Cout]
 };
@@ -63,19 +69,25 @@ template <int BN, int MODE>
 struct ConvCfg {
   static constexpr int ROWB = (MODE == MODE_STEM) ? 64 : 128;  // bytes per smem operand row (= BLOCK_K bf16)
   static constexpr int BLOCK_K = ROWB / 2;
-  static constexpr int A_BYTES = kBlockM * ROWB;
+  static constexpr int A_BYTES = (MODE == MODE_HALO) ? 0 : kBlockM * ROWB;  // HALO: A lives in the patch buffers
   static constexpr int B_BYTES = BN * ROWB;
+  // MODE_HALO patch buffers: (R_t+2) x (W+2) positions x 128 B, sized so the furthest shifted 128-row window stays
+  // inside: 56x56 (BN=64): 4x58 = 232 loaded, 118+128 = 246 read -> 32 KB; 28x28 (BN=128): 6x30 = 180, 62+128 = 190
+  // read -> 24 KB
+  static constexpr int HALO_BYTES = (MODE == MODE_HALO) ? (BN == 64 ? 32768 : 24576) : 0;
+  static constexpr int HB = (MODE == MODE_HALO) ? (BN == 64 ? 3 : 4) : 0;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int A_TX = ((MODE == MODE_GAP) ? kGapRows : kBlockM) * ROWB;
-  static constexpr int NB = (MODE == MODE_GAP) ? 2 : 4;        // epilogue staging buffers
+  static constexpr int NB = (MODE == MODE_GAP || MODE == MODE_HALO) ? 2 : 4;  // epilogue staging buffers
   static constexpr int LOOK = (NB == 2) ? 1 : 2;               // residual loads run LOOK groups ahead of the stores
   static constexpr int GROUPS = BN / kGroupCols;
   static constexpr int SCRATCH_BYTES = (MODE == MODE_GAP) ? 2 * kBlockM * 33 * 4 : 0;
   static constexpr int TAIL_BYTES = 1024 + 2 * BN * 4 + SCRATCH_BYTES;  // barriers + bias double buffer + scratch
   static constexpr int SMEM_MAX = 232448;                              // 227 KB
-  static constexpr int NSTAGE_RAW = (SMEM_MAX - 1024 - TAIL_BYTES - NB * kStageOutBytes) / STAGE_BYTES;
+  static constexpr int NSTAGE_RAW =
+      (SMEM_MAX - 1024 - TAIL_BYTES - NB * kStageOutBytes - HB * HALO_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + NB * kStageOutBytes + TAIL_BYTES + 1024;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + HB * HALO_BYTES + NB * kStageOutBytes + TAIL_BYTES + 1024;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
 };
 
@@ -89,12 +101,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   constexpr int NB = Cfg::NB;
   constexpr int LOOK = Cfg::LOOK;
   constexpr int GROUPS = Cfg::GROUPS;
+  constexpr int HBD = Cfg::HB > 0 ? Cfg::HB : 1;  // patch-buffer count (1 keeps dead non-HALO code well-formed)
   static_assert(NSTAGE >= 2, "pipeline needs at least two stages");
   static_assert(Cfg::SMEM_BYTES <= Cfg::SMEM_MAX, "shared memory budget exceeded");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_out = smem + NSTAGE * Cfg::STAGE_BYTES;  // [NB][128][128 B], 1024-aligned
+  uint8_t* halo = smem + NSTAGE * Cfg::STAGE_BYTES;       // MODE_HALO: [HB] input patches, 1024-aligned
+  uint8_t* stage_out = halo + Cfg::HB * Cfg::HALO_BYTES;  // [NB][128][128 B], 1024-aligned
   uint8_t* tail = stage_out + NB * kStageOutBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);  // [NSTAGE]
   uint64_t* empty_bar = full_bar + NSTAGE;                 // [NSTAGE]
@@ -102,7 +116,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;                    // [2]
   uint64_t* res_full = tmem_empty + 2;                     // [NB] staging buffer holds the residual / is free
   uint64_t* out_full = res_full + NB;                      // [NB] epilogue warps are done with the buffer
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_full + NB);
+  uint64_t* halo_full = out_full + NB;                     // [HB]
+  uint64_t* halo_empty = halo_full + (Cfg::HB > 0 ? Cfg::HB : 1);  // [HB]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(halo_empty + (Cfg::HB > 0 ? Cfg::HB : 1));
   float* s_bias = reinterpret_cast<float*>(tail + 1024);   // [2][BN]
   float* s_scratch = s_bias + 2 * BN;                      // MODE_GAP: [2 halves][128][33]
 
@@ -131,6 +147,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       mbar_init(&res_full[i], 1);
       mbar_init(&out_full[i], kEpiWarps);
     }
+    for (int i = 0; i < Cfg::HB; ++i) {
+      mbar_init(&halo_full[i], 1);
+      mbar_init(&halo_empty[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -151,6 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     {  // whole warp, warp-uniform control flow; one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
+      int hseq = 0;  // MODE_HALO: patches loaded so far
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.n_tiles;
         const int n_blk = tile - m_blk * p.n_tiles;
@@ -170,8 +191,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const int t = m_blk - cn * kStemTilesPerFrame;
           ch = (t / (kStemOut / kStemTileQ)) * kStemTileP;  // p0
           cw = (t % (kStemOut / kStemTileQ)) * kStemTileQ;  // q0
+        } else if (MODE == MODE_HALO) {
+          const int tpf = p.P / p.halo_rt;  // tiles per frame
+          cn = m_blk / tpf;
+          ch = (m_blk - cn * tpf) * p.halo_rt - 1;  // first input row of the patch (-1 = zero halo)
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (MODE == MODE_HALO) {
+            // kb = cb * 9 + tap: one input patch per 64-channel block, then its nine weight tiles
+            const int cb = kb / 9;
+            const int tap = kb - cb * 9;
+            if (tap == 0) {
+              const int hb = hseq % HBD;
+              mbar_wait(&halo_empty[hb], ((hseq / HBD) & 1) ^ 1);
+              mbar_arrive_expect_tx_elect(&halo_full[hb], 128 * (p.Q + 2) * (p.halo_rt + 2));
+              tma_load_4d_elect(&mapA, &halo_full[hb], halo + hb * Cfg::HALO_BYTES, cb * 64, -1, ch, cn);
+              ++hseq;
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx_elect(&full_bar[stage], Cfg::B_BYTES);
+            tma_load_2d_elect(&mapB, &full_bar[stage], smem + stage * Cfg::STAGE_BYTES,
+                              (tap * p.kb_per_tap + cb) * 64, n_blk * BN);
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
@@ -210,15 +256,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int hseq = 0;  // MODE_HALO: patches consumed so far
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          int tap = 0;
+          if (MODE == MODE_HALO) {
+            tap = kb % 9;
+            if (tap == 0) mbar_wait(&halo_full[hseq % HBD], (hseq / HBD) & 1);
+          }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          if (MODE == MODE_HALO) {
+            // tap (r, s): the same patch, shifted by r rows and s pixels of the padded raster
+            const int r = tap / 3;
+            const int sft = r * (p.Q + 2) + (tap - r * 3);
+            a_addr = smem_u32(halo + (hseq % HBD) * Cfg::HALO_BYTES) + sft * 128;
+          }
 #pragma unroll
           for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
             const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, Cfg::ROWB);
@@ -226,6 +284,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             umma_bf16_elect(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_elect(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (MODE == MODE_HALO && tap == 8) {
+            umma_commit_elect(&halo_empty[hseq % HBD]);  // all nine taps of this patch have been issued
+            ++hseq;
+          }
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -280,6 +342,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               const int p0 = (tt / (kStemOut / kStemTileQ)) * kStemTileP;
               const int q0 = (tt % (kStemOut / kStemTileQ)) * kStemTileQ;
               tma_store_4d(&mapO, src, 0, q0, p0, n);
+            } else if (MODE == MODE_HALO) {
+              const int tpf = p.P / p.halo_rt;
+              const int n = m_blk / tpf;
+              tma_store_4d(&mapO, src, n_blk * BN + g * kGroupCols, 0, (m_blk - n * tpf) * p.halo_rt, n);
             } else {
               tma_store_2d(&mapO, src, n_blk * BN + g * kGroupCols, m_blk * kBlockM);
             }
@@ -309,6 +375,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
       bool row_ok = true;
       if (MODE == MODE_GAP) row_ok = (row < kGapRows) && (m_blk * kGapRows + row < p.M);
+      int srow = row;  // row of the staging buffer this thread writes
+      if (MODE == MODE_HALO) {
+        // tile row = padded-raster position i*(W+2)+j; only j < W, i < R_t are outputs; staging is dense [R_t][W]
+        const int wp = p.Q + 2;
+        const int i = row / wp;
+        const int j = row - i * wp;
+        row_ok = (i < p.halo_rt) && (j < p.Q);
+        srow = i * p.Q + j;
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -318,7 +393,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int g = 0; g < GROUPS; ++g, ++jg) {
         const int b = jg % NB;
         mbar_wait(&res_full[b], (jg / NB) & 1);
-        uint8_t* row_ptr = stage_out + b * kStageOutBytes + row * 128;
+        uint8_t* row_ptr = stage_out + b * kStageOutBytes + srow * 128;
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + g * kGroupCols + half * 32, v);
         tmem_ld_wait();
@@ -326,7 +401,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           // 16-byte chunk (8 channels) of this thread's row; 128B-swizzle: physical chunk = logical ^ (row & 7)
-          uint4* sp = reinterpret_cast<uint4*>(row_ptr + (((half * 4 + c4) ^ (row & 7)) << 4));
+          uint4* sp = reinterpret_cast<uint4*>(row_ptr + (((half * 4 + c4) ^ (srow & 7)) << 4));
           const float4 b0 = sb4[2 * c4], b1 = sb4[2 * c4 + 1];
           float f[8];
           f[0] = __uint_as_float(v[8 * c4 + 0]) + b0.x;
@@ -371,7 +446,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             o.y = *reinterpret_cast<uint32_t*>(&o2[1]);
             o.z = *reinterpret_cast<uint32_t*>(&o2[2]);
             o.w = *reinterpret_cast<uint32_t*>(&o2[3]);
-            *sp = o;
+            if (MODE != MODE_HALO || row_ok) *sp = o;
           }
         }
         if (MODE == MODE_GAP) {

@@ -227,6 +227,18 @@ __device__ __forceinline__ void tma_load_3d_elect(const CUtensorMap* m, uint64_t
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_elect(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                  int c2, int c3) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d_elect(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
                                                   int c2, int c3, int c4) {
   asm volatile(
