@@ -86,7 +86,10 @@ struct ConvCfg {
   static constexpr int SMEM_MAX = 232448;                              // 227 KB
   static constexpr int NSTAGE_RAW =
       (SMEM_MAX - 1024 - TAIL_BYTES - NB * kStageOutBytes - HB * HALO_BYTES) / STAGE_BYTES;
-  static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
+  // MODE_HALO with BN = 64 (layer1: Cin = Cout = 64): the nine 8 KB weight tiles stay RESIDENT in the nine "stages" for
+  // the whole kernel (loaded once), so per tile only the input patch moves.
+  static constexpr bool RES_B = (MODE == MODE_HALO && BN == 64);
+  static constexpr int NSTAGE = RES_B ? 9 : (NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW);
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + HB * HALO_BYTES + NB * kStageOutBytes + TAIL_BYTES + 1024;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
 };
@@ -172,6 +175,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int hseq = 0;  // MODE_HALO: patches loaded so far
+      if (Cfg::RES_B) {
+        for (int tap = 0; tap < 9; ++tap) {  // resident weights: tile `tap` -> stage `tap`, loaded once
+          mbar_arrive_expect_tx_elect(&full_bar[tap], Cfg::B_BYTES);
+          tma_load_2d_elect(&mapB, &full_bar[tap], smem + tap * Cfg::STAGE_BYTES, tap * 64, 0);
+        }
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.n_tiles;
         const int n_blk = tile - m_blk * p.n_tiles;
@@ -208,6 +217,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               tma_load_4d_elect(&mapA, &halo_full[hb], halo + hb * Cfg::HALO_BYTES, cb * 64, -1, ch, cn);
               ++hseq;
             }
+            if (Cfg::RES_B) continue;  // weights are resident
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx_elect(&full_bar[stage], Cfg::B_BYTES);
             tma_load_2d_elect(&mapB, &full_bar[stage], smem + stage * Cfg::STAGE_BYTES,
@@ -257,17 +267,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       int acc = 0;
       uint32_t acc_phase = 0;
       int hseq = 0;  // MODE_HALO: patches consumed so far
+      bool res_b_ready = false;  // RES_B: the nine resident weight tiles have landed (checked during the first tile)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        // `ready`: the barrier of the stage about to be consumed is already known to be complete (probed while the
+        // previous K block's MMAs were being issued), so the ~90-cycle query is off the issue path
+        bool ready = false;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           int tap = 0;
           if (MODE == MODE_HALO) {
             tap = kb % 9;
             if (tap == 0) mbar_wait(&halo_full[hseq % HBD], (hseq / HBD) & 1);
           }
-          mbar_wait(&full_bar[stage], phase);
+          if (Cfg::RES_B) {
+            stage = tap;  // resident weight tile; its barrier completed phase 0 once and never advances
+            phase = 0;
+            if (!res_b_ready) mbar_wait(&full_bar[stage], 0);
+          } else if (!ready) {
+            mbar_wait(&full_bar[stage], phase);
+          }
           tc_fence_after();
           uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
@@ -277,22 +297,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const int sft = r * (p.Q + 2) + (tap - r * 3);
             a_addr = smem_u32(halo + (hseq % HBD) * Cfg::HALO_BYTES) + sft * 128;
           }
-#pragma unroll
-          for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
-            const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, Cfg::ROWB);
-            const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, Cfg::ROWB);
-            umma_bf16_elect(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          // probe the next stage before issuing (non-blocking)
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == NSTAGE) {
+            nstage = 0;
+            nphase ^= 1;
           }
-          umma_commit_elect(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          ready = false;
+          if (!Cfg::RES_B && kb + 1 < p.num_kb) ready = mbar_test(&full_bar[nstage], nphase);
+          // descriptors once per K block; each K=16 step advances the start address by 32 B (field unit 16 B)
+          const uint64_t adesc0 = make_kmajor_desc(a_addr, Cfg::ROWB);
+          const uint64_t bdesc0 = make_kmajor_desc(b_addr, Cfg::ROWB);
+          if (Cfg::BLOCK_K == 64)
+            umma_bf16_x4_elect(d_tmem, adesc0, bdesc0, idesc, kb != 0 ? 1u : 0u);
+          else
+            umma_bf16_x2_elect(d_tmem, adesc0, bdesc0, idesc, kb != 0 ? 1u : 0u);
+          if (!Cfg::RES_B) umma_commit_elect(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (MODE == MODE_HALO && tap == 8) {
             umma_commit_elect(&halo_empty[hseq % HBD]);  // all nine taps of this patch have been issued
             ++hseq;
           }
-          if (++stage == NSTAGE) {
-            stage = 0;
-            phase ^= 1;
+          if (!Cfg::RES_B) {
+            stage = nstage;
+            phase = nphase;
           }
         }
+        res_b_ready = true;
         umma_commit_elect(&tmem_full[acc]);  // accumulator complete
         if (++acc == 2) {
           acc = 0;

@@ -57,6 +57,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// Non-blocking probe: has the phase with this parity completed?  Used to overlap the ~90-cycle barrier query of the
+// NEXT pipeline stage with issuing the current stage's MMAs.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -184,6 +200,63 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc,
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One K block = four (or two) K=16 MMAs issued back to back under ONE election; each step advances both descriptors'
+// start-address fields by 2 (= 32 bytes).  Keeping the whole group in one asm block keeps the per-MMA issue cost to a
+// couple of uniform instructions (it is the single MMA-issuing warp that bounds small-N layers).
+__device__ __forceinline__ void umma_bf16_x4_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pe, pt;\n"
+      ".reg .b32 alo, ahi, blo, bhi;\n"
+      ".reg .b64 da, db;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "mov.b64 {alo, ahi}, %1;\n"
+      "mov.b64 {blo, bhi}, %2;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "add.u32 alo, alo, 2;\n"
+      "add.u32 blo, blo, 2;\n"
+      "mov.b64 da, {alo, ahi};\n"
+      "mov.b64 db, {blo, bhi};\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n"
+      "add.u32 alo, alo, 2;\n"
+      "add.u32 blo, blo, 2;\n"
+      "mov.b64 da, {alo, ahi};\n"
+      "mov.b64 db, {blo, bhi};\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n"
+      "add.u32 alo, alo, 2;\n"
+      "add.u32 blo, blo, 2;\n"
+      "mov.b64 da, {alo, ahi};\n"
+      "mov.b64 db, {blo, bhi};\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_x2_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pe, pt;\n"
+      ".reg .b32 alo, ahi, blo, bhi;\n"
+      ".reg .b64 da, db;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "mov.b64 {alo, ahi}, %1;\n"
+      "mov.b64 {blo, bhi}, %2;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "add.u32 alo, alo, 2;\n"
+      "add.u32 blo, blo, 2;\n"
+      "mov.b64 da, {alo, ahi};\n"
+      "mov.b64 db, {blo, bhi};\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
