@@ -11,6 +11,7 @@
 
 #include "../../include/phdfx.h"
 #include "conv_igemm_sm100.cuh"
+#include "conv_igemm_cg2_sm100.cuh"
 #include "elementwise_sm100.cuh"
 #include "stem_pool_sm100.cuh"
 
@@ -125,8 +126,10 @@ struct Geo {
   int K;           // GEMM K (packed)
   int num_kb;
   int halo_rt;     // MODE_HALO: output rows per tile
+  bool cg2;        // run on CTA pairs (tcgen05 cta_group::2): each SM loads half of the 256-row weight tile
 };
 
+bool g_use_cg2 = true;   // PHDFX_NO_CG2=1: keep the K-heavy layers on the 1-CTA kernel
 bool g_use_halo = true;  // PHDFX_NO_HALO=1 (read at phdfx_create) falls back to the im2col path for A/B measurements
 
 Geo geometry(const phdfx_layer_desc& L) {
@@ -152,6 +155,8 @@ Geo geometry(const phdfx_layer_desc& L) {
     } else
       g.mode = MODE_IM2COL;
     g.bn = L.cout >= 256 ? 256 : L.cout;
+    g.cg2 = g_use_cg2 && (g.mode == MODE_TILED || g.mode == MODE_IM2COL) && g.bn == 256 && L.res_buf < 0 &&
+            !L.gap && g.num_kb >= 8;
   }
   return g;
 }
@@ -274,7 +279,7 @@ int build_maps(phdfx_t* h, const phdfx_layer_desc& L, const void* in, const void
   }
   cuuint64_t wd[2] = {static_cast<cuuint64_t>(g.K), static_cast<cuuint64_t>(L.cout)};
   cuuint64_t ws[1] = {static_cast<cuuint64_t>(g.K) * 2};
-  cuuint32_t wb[2] = {64, static_cast<cuuint32_t>(g.bn)};
+  cuuint32_t wb[2] = {64, static_cast<cuuint32_t>(g.cg2 ? g.bn / 2 : g.bn)};  // CTA pairs: half a weight tile per SM
   if (int rc = encode_tiled(h, &out->b, w, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B, "W")) return rc;
   out->valid = true;
   return 0;
@@ -293,6 +298,23 @@ int launch_conv_t(phdfx_t* h, const LayerMaps& maps, const ConvParams& p, cudaSt
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
   CUDA_TRY(h, launch_pdl(conv_igemm_kernel<BN, MODE>, dim3(grid), dim3(kNumThreads), Cfg::SMEM_BYTES, st, maps.a,
                          maps.b, maps.o, maps.r, p));
+  h->last_launches++;
+  return 0;
+}
+
+template <int MODE>
+int launch_conv_cg2_t(phdfx_t* h, const LayerMaps& maps, const ConvParams& p, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(conv_igemm_cg2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cg2Cfg::SMEM_BYTES));
+    attr_set[h->device & 63] = true;
+  }
+  const int ptiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int max_pairs = h->num_sms / 2;
+  const int pairs = ptiles < max_pairs ? ptiles : max_pairs;
+  CUDA_TRY(h, launch_pdl(conv_igemm_cg2_kernel<MODE>, dim3(2 * pairs), dim3(kNumThreads), Cg2Cfg::SMEM_BYTES, st,
+                         maps.a, maps.b, maps.o, p));
   h->last_launches++;
   return 0;
 }
@@ -326,6 +348,10 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bo
   else
     p.m_tiles = (p.M + kBlockM - 1) / kBlockM;
 
+  if (g.cg2) {
+    if (g.mode == MODE_TILED) return launch_conv_cg2_t<MODE_TILED>(h, maps, p, st);
+    return launch_conv_cg2_t<MODE_IM2COL>(h, maps, p, st);
+  }
   switch (g.mode) {
     case MODE_STEM:
       return launch_conv_t<64, MODE_STEM>(h, maps, p, st);
@@ -425,6 +451,7 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   *out = nullptr;
   if (max_frames < 1) return fail(nullptr, PHDFX_ERR_INVALID, "max_frames must be >= 1");
   if (const char* e = getenv("PHDFX_NO_HALO")) g_use_halo = !(e[0] == '1');
+  if (const char* e = getenv("PHDFX_NO_CG2")) g_use_cg2 = !(e[0] == '1');
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
