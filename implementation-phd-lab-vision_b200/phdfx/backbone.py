@@ -129,6 +129,10 @@ class B200Backbone:
         self.launches = launches
         return feats
 
+    def capture(self, fn) -> "CapturedCall":
+        """Capture an arbitrary sequence of engine calls on fixed tensors (fn()) into a CUDA graph."""
+        return CapturedCall(self, fn)
+
     def capture_extract(self, frames: torch.Tensor, boxes: Optional[torch.Tensor] = None, flip_w: bool = False,
                         out: Optional[torch.Tensor] = None) -> "ExtractGraph":
         """Capture extract_u8 on exactly these tensors into a CUDA graph (54 launches -> one graph launch)."""
@@ -224,3 +228,21 @@ class ExtractGraph:
     def replay(self) -> torch.Tensor:
         self.graph.replay()
         return self.out
+
+
+class CapturedCall:
+    """fn() — engine calls on fixed tensors — frozen into a CUDA graph (see ExtractGraph)."""
+
+    def __init__(self, eng: B200Backbone, fn):
+        side = torch.cuda.Stream(eng.device)
+        side.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream(eng.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.result
