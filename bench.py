@@ -270,6 +270,14 @@ def run_b200(args):
     trunk_ms = e0.elapsed_time(e1) / reps
     pk = peaks()
     achieved_tf = BATCH * FLOP_PER_FRAME / (trunk_ms / 1e3) / 1e12
+    # DRAM traffic of the trunk's launches, from the committed `ncu --set full` capture of one step (not measured live)
+    traffic = None
+    for cand in sorted((ROOT / "profiles").glob("r*/trunk_traffic_*.json")):
+        try:
+            traffic = json.loads(cand.read_text())
+            traffic["file"] = str(cand.relative_to(ROOT))
+        except Exception:  # noqa: BLE001
+            pass
 
     # ---- K1 alone (HBM-bound) ----------------------------------------------------------------------------------
     k1_out = x4s[0]
@@ -332,7 +340,11 @@ def run_b200(args):
                     "api": "phdfx.StreamingExtractor (pinned host uint8 -> features in pinned host fp32)"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved_tf / pk["bf16_sustained"], "traffic": None,
+                         "frac": achieved_tf / pk["bf16_sustained"],
+                         "traffic": traffic["traffic_bytes_per_step"] if traffic else None,
+                         "traffic_source": (traffic["file"] + " (ncu dram__bytes_read+write summed over the trunk's "
+                                            "launches of one step)") if traffic else None,
+                         "algorithmic_bytes_per_step_unfused": 256 * 54_600_000,
                          "kernel": "trunk = stem_pool_kernel (1 launch) + conv_igemm_kernel (52 launches) per step",
                          "trunk_ms_per_step": trunk_ms, "flop_per_frame": FLOP_PER_FRAME,
                          "frac_of_burst_peak": achieved_tf / pk["bf16_burst"], "peak_burst": pk["bf16_burst"],
