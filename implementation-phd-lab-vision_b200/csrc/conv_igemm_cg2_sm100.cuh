@@ -135,7 +135,8 @@ struct Cg2Cfg {
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                      const __grid_constant__ CUtensorMap mapO, const ConvParams p) {
+                      const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapA2,
+                      const ConvParams p) {
   using Cfg = Cg2Cfg;
   constexpr int BN = Cfg::BN;
   constexpr int NSTAGE = Cfg::NSTAGE;
@@ -207,15 +208,20 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const int n_blk = pt - m_pair * p.n_tiles;
       const int m_blk = 2 * m_pair + static_cast<int>(rank);
       int cw = 0, ch = 0, cn = 0;
-      if (MODE == MODE_IM2COL) {
+      if (MODE == MODE_IM2COL || p.src2_stride == 2) {
         const int m0 = m_blk * kBlockM;
         const int pq = p.P * p.Q;
         cn = m0 / pq;
         const int rem = m0 - cn * pq;
         const int p0 = rem / p.Q;
         const int q0 = rem - p0 * p.Q;
-        cw = q0 * p.stride - p.pad;
-        ch = p0 * p.stride - p.pad;
+        if (MODE == MODE_IM2COL) {
+          cw = q0 * p.stride - p.pad;
+          ch = p0 * p.stride - p.pad;
+        } else {  // fused stride-2 down-sample as the second source of a 1x1 conv
+          cw = q0 * 2;
+          ch = p0 * 2;
+        }
       }
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -224,7 +230,12 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         // the leader arms its barrier with the bytes of BOTH CTAs
         if (leader) mbar_arrive_expect_tx_elect(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
         if (MODE == MODE_TILED) {
-          tma_load_2d_cg2_elect(&mapA, &full_bar[stage], sA, kb * 64, m_blk * kBlockM);
+          if (kb < p.kb_split)
+            tma_load_2d_cg2_elect(&mapA, &full_bar[stage], sA, kb * 64, m_blk * kBlockM);
+          else if (p.src2_stride == 1)
+            tma_load_2d_cg2_elect(&mapA2, &full_bar[stage], sA, (kb - p.kb_split) * 64, m_blk * kBlockM);
+          else
+            tma_load_im2col_4d_cg2_elect(&mapA2, &full_bar[stage], sA, (kb - p.kb_split) * 64, cw, ch, cn, 0, 0);
         } else {
           const int tap = kb / p.kb_per_tap;
           const int cb = kb - tap * p.kb_per_tap;

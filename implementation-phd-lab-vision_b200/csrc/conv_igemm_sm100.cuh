@@ -51,6 +51,9 @@ struct ConvParams {
   int has_res;     // residual tile is TMA-loaded through mapR
   int n_frames;
   int halo_rt;     // MODE_HALO: output rows per tile (2 for 56x56, 4 for 28x28)
+  int kb_split;    // MODE_TILED with a second source (fused down-sample): K blocks [0, kb_split) come from mapA,
+                   // [kb_split, num_kb) from mapA2; = num_kb when there is no second source
+  int src2_stride; // second source: 1 = tiled 2-D map over its activation matrix, 2 = im2col map (1x1 stride 2)
   const float* bias;  // [Cout] folded BN bias
   float* feats;       // MODE_GAP: [n_frames, Cout]
 };
@@ -98,7 +101,7 @@ template <int BN, int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapR,
-                  const ConvParams p) {
+                  const __grid_constant__ CUtensorMap mapA2, const ConvParams p) {
   using Cfg = ConvCfg<BN, MODE>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   constexpr int NB = Cfg::NB;
@@ -132,6 +135,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    if (MODE == MODE_TILED && p.kb_split < p.num_kb) tma_prefetch_desc(&mapA2);
   }
   if (warp == 2 && lane == 0) {
     if (MODE != MODE_GAP) tma_prefetch_desc(&mapO);
@@ -186,15 +190,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int n_blk = tile - m_blk * p.n_tiles;
         // per-tile A coordinates
         int cw = 0, ch = 0, cn = 0;
-        if (MODE == MODE_IM2COL) {
+        if (MODE == MODE_IM2COL || (MODE == MODE_TILED && p.src2_stride == 2)) {
+          // base pixel of the tile in the (second) source's input coordinates; for the fused stride-2 down-sample
+          // pad is 0 and stride 2
           const int m0 = m_blk * kBlockM;
           const int pq = p.P * p.Q;
           cn = m0 / pq;
           const int rem = m0 - cn * pq;
           const int p0 = rem / p.Q;
           const int q0 = rem - p0 * p.Q;
-          cw = q0 * p.stride - p.pad;
-          ch = p0 * p.stride - p.pad;
+          if (MODE == MODE_IM2COL) {
+            cw = q0 * p.stride - p.pad;
+            ch = p0 * p.stride - p.pad;
+          } else {
+            cw = q0 * 2;
+            ch = p0 * 2;
+          }
         } else if (MODE == MODE_STEM) {
           cn = m_blk / kStemTilesPerFrame;
           const int t = m_blk - cn * kStemTilesPerFrame;
@@ -233,7 +244,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           uint8_t* sB = sA + Cfg::A_BYTES;
           mbar_arrive_expect_tx_elect(&full_bar[stage], Cfg::A_TX + Cfg::B_BYTES);
           if (MODE == MODE_TILED) {
-            tma_load_2d_elect(&mapA, &full_bar[stage], sA, kb * Cfg::BLOCK_K, m_blk * kBlockM);
+            if (kb < p.kb_split)
+              tma_load_2d_elect(&mapA, &full_bar[stage], sA, kb * Cfg::BLOCK_K, m_blk * kBlockM);
+            else if (p.src2_stride == 1)
+              tma_load_2d_elect(&mapA2, &full_bar[stage], sA, (kb - p.kb_split) * Cfg::BLOCK_K, m_blk * kBlockM);
+            else
+              tma_load_im2col_4d_elect(&mapA2, &full_bar[stage], sA, (kb - p.kb_split) * Cfg::BLOCK_K, cw, ch, cn, 0,
+                                       0);
             tma_load_2d_elect(&mapB, &full_bar[stage], sB, kb * Cfg::BLOCK_K, n_blk * BN);
           } else if (MODE == MODE_IM2COL) {
             const int tap = kb / p.kb_per_tap;

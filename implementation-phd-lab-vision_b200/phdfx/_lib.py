@@ -23,6 +23,7 @@ EXPORTS = [
     "phdfx_forward",
     "phdfx_extract_u8",
     "phdfx_run_layer",
+    "phdfx_run_layer2",
     "phdfx_layer_count",
     "phdfx_layer_info",
     "phdfx_last_launch_count",
@@ -50,6 +51,10 @@ class LayerDesc(C.Structure):
         ("out_buf", C.c_int32),
         ("res_buf", C.c_int32),
         ("gap", C.c_int32),
+        ("in2_buf", C.c_int32),
+        ("cin2", C.c_int32),
+        ("stride2", C.c_int32),
+        ("hin2", C.c_int32),
         ("w_off", C.c_int64),
         ("b_off", C.c_int64),
     ]
@@ -94,6 +99,8 @@ def load() -> C.CDLL:
     lib.phdfx_extract_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp]
     lib.phdfx_run_layer.restype = i32
     lib.phdfx_run_layer.argtypes = [vp, i32, vp, vp, vp, i32, vp]
+    lib.phdfx_run_layer2.restype = i32
+    lib.phdfx_run_layer2.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
     lib.phdfx_layer_count.restype = i32
     lib.phdfx_layer_count.argtypes = [vp]
     lib.phdfx_layer_info.restype = i32

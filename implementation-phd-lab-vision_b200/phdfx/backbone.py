@@ -24,7 +24,7 @@ class B200Backbone:
     FEAT_DIM = _lib.FEAT_DIM
 
     def __init__(self, backbone: nn.Module, device: "int | str | torch.device" = 0, max_frames: int = 1280,
-                 fuse_stem_pool: bool = True):
+                 fuse_stem_pool: bool = True, fuse_downsample: bool = True):
         self._lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("B200Backbone needs a CUDA device (sm_100); this backend has no CPU fallback")
@@ -33,7 +33,7 @@ class B200Backbone:
             raise RuntimeError(f"B200Backbone cannot run on {dev}; this backend has no CPU fallback")
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.max_frames = int(max_frames)
-        self.plan: Plan = build_plan(backbone, fuse_stem_pool=fuse_stem_pool)
+        self.plan: Plan = build_plan(backbone, fuse_stem_pool=fuse_stem_pool, fuse_downsample=fuse_downsample)
         self._h = C.c_void_p()
         _lib.check(self._lib.phdfx_create(C.byref(self._h), self.device.index, self.max_frames))
         arr = (_lib.LayerDesc * len(self.plan.layers))(*self.plan.layers)
@@ -175,8 +175,10 @@ class B200Backbone:
 
     # ---- per-layer hook --------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def run_layer(self, layer_id: int, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Run one entry of the execution list on explicit tensors (NHWC bf16; NHWC4p for the stem)."""
+    def run_layer(self, layer_id: int, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                  x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Run one entry of the execution list on explicit tensors (NHWC bf16; NHWC4p for the stem); x2 = the second
+        input of a fused conv3+downsample layer."""
         L = self.plan.layers[layer_id]
         n = x.shape[0]
         self._check_dev(x, "x")
@@ -195,9 +197,13 @@ class B200Backbone:
         if residual is not None:
             self._check_dev(residual, "residual")
             rp = residual.data_ptr()
+        x2p = None
+        if x2 is not None:
+            self._check_dev(x2, "x2")
+            x2p = x2.data_ptr()
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.phdfx_run_layer(self._h, layer_id, x.data_ptr(), rp, out.data_ptr(), n,
-                                                 self._stream()), self._h)
+            _lib.check(self._lib.phdfx_run_layer2(self._h, layer_id, x.data_ptr(), x2p, rp, out.data_ptr(), n,
+                                                  self._stream()), self._h)
         return out
 
 

@@ -80,9 +80,12 @@ def _children(backbone: nn.Module):
                                                             backbone.layer4]
 
 
-def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True) -> Plan:
+def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample: bool = True) -> Plan:
     """fuse_stem_pool=True (default): conv1+bn1+relu+maxpool is ONE launch (stem_pool_sm100.cuh).  False keeps the
-    separate implicit-GEMM stem and max-pool kernels (used for A/B measurements and their own parity tests)."""
+    separate implicit-GEMM stem and max-pool kernels (used for A/B measurements and their own parity tests).
+    fuse_downsample=True (default): in the first block of each stage the down-sample branch is accumulated into
+    conv3's GEMM (K concatenated, weights [cout][width + cin], bias b3 + bd) instead of being a launch and a tensor
+    of its own:  out = relu(conv3(t2) + downsample(x))  (resnet.py:154-161)."""
     conv1, bn1, maxpool, stages = _children(backbone)
     chunks, biases, layers, names = [], [], [], []
     w_cursor = 0
@@ -103,7 +106,7 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True) -> Plan:
     def desc(**kw) -> LayerDesc:
         d = LayerDesc()
         base = dict(kind=PHDFX_CONV, cin=0, cout=0, r=1, s=1, stride=1, pad=0, hin=0, win=0, relu=0, in_buf=0,
-                    out_buf=0, res_buf=-1, gap=0, w_off=0, b_off=0)
+                    out_buf=0, res_buf=-1, gap=0, in2_buf=-1, cin2=0, stride2=1, hin2=0, w_off=0, b_off=0)
         base.update(kw)
         for k, v in base.items():
             setattr(d, k, int(v))
@@ -152,21 +155,32 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True) -> Plan:
             names.append(name + ".conv2")
             ho = (h + 2 - 3) // stride + 1
             res_buf = x_buf
-            if blk.downsample is not None:
-                # downsample 1x1/stride + bn, no relu (resnet.py:157-158, 239-243)
+            w3, b3 = fold_conv_bn(blk.conv3, blk.bn3)
+            if blk.downsample is not None and fuse_downsample:
+                # conv3 and the down-sample branch write the same pixels: one GEMM over K = width + cin
                 dconv, dbn = blk.downsample[0], blk.downsample[1]
-                w, b = fold_conv_bn(dconv, dbn)
-                w_off, b_off = add_weights(pack_conv(w), b)
-                layers.append(desc(cin=cin, cout=cout, stride=dconv.stride[0], hin=h, win=h, relu=0, in_buf=x_buf,
-                                   out_buf=5, w_off=w_off, b_off=b_off))
-                names.append(name + ".downsample")
-                res_buf = 5
-            # conv3 1x1 + bn3 + residual + relu (:154-161); the last one also fuses avgpool (:278)
-            w, b = fold_conv_bn(blk.conv3, blk.bn3)
-            w_off, b_off = add_weights(pack_conv(w), b)
-            layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=4, out_buf=o_buf,
-                               res_buf=res_buf, gap=1 if last else 0, w_off=w_off, b_off=b_off))
-            names.append(name + ".conv3")
+                wd, bd = fold_conv_bn(dconv, dbn)
+                wcat = torch.cat([w3.reshape(cout, width), wd.reshape(cout, cin)], dim=1)  # [cout][width | cin]
+                w_off, b_off = add_weights(wcat.contiguous().to(torch.bfloat16).reshape(-1), b3 + bd)
+                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=4, out_buf=o_buf, res_buf=-1,
+                                   gap=1 if last else 0, in2_buf=x_buf, cin2=cin, stride2=dconv.stride[0], hin2=h,
+                                   w_off=w_off, b_off=b_off))
+                names.append(name + ".conv3+downsample")
+            else:
+                if blk.downsample is not None:
+                    # downsample 1x1/stride + bn, no relu (resnet.py:157-158, 239-243)
+                    dconv, dbn = blk.downsample[0], blk.downsample[1]
+                    w, b = fold_conv_bn(dconv, dbn)
+                    w_off, b_off = add_weights(pack_conv(w), b)
+                    layers.append(desc(cin=cin, cout=cout, stride=dconv.stride[0], hin=h, win=h, relu=0,
+                                       in_buf=x_buf, out_buf=5, w_off=w_off, b_off=b_off))
+                    names.append(name + ".downsample")
+                    res_buf = 5
+                # conv3 1x1 + bn3 + residual + relu (:154-161); the last one also fuses avgpool (:278)
+                w_off, b_off = add_weights(pack_conv(w3), b3)
+                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=4, out_buf=o_buf,
+                                   res_buf=res_buf, gap=1 if last else 0, w_off=w_off, b_off=b_off))
+                names.append(name + ".conv3")
             x_buf, o_buf = o_buf, x_buf
             h = ho
     return Plan(weights=torch.cat(chunks).contiguous(), bias=torch.cat(biases).contiguous(), layers=layers,

@@ -55,6 +55,10 @@ typedef struct phdfx_layer_desc {
   int32_t in_buf, out_buf; /* arena buffer ids */
   int32_t res_buf;         /* residual added before ReLU; -1 = none */
   int32_t gap;             /* 1: fuse AdaptiveAvgPool2d(1) (resnet.py:278): emit fp32 [n, cout] features */
+  /* Optional second 1x1 source accumulated into the same output (K concatenated): the block's down-sample branch
+   * (resnet.py:157-158, 239-243) fused into conv3:  out = relu(conv3(t2) + downsample(x) + b3 + bd).
+   * in2_buf = -1: none.  The layer itself must then be a 1x1 stride-1 conv; weights are [cout][cin + cin2]. */
+  int32_t in2_buf, cin2, stride2, hin2; /* second input buffer, its channels, its stride (1 or 2), its spatial size */
   int64_t w_off;           /* element offset of this layer's packed weights [cout][r][s][cin] (stem: [7][64][32]) */
   int64_t b_off;           /* element offset of this layer's folded-BN bias [cout] */
 } phdfx_layer_desc;
@@ -101,6 +105,9 @@ int phdfx_extract_u8(phdfx_t* h, const uint8_t* d_frames_hwc, int n, int H, int 
  * layouts: NHWC bf16 activations (NHWC4p for the stem input); for a gap layer d_out is fp32 [n][cout]. */
 int phdfx_run_layer(phdfx_t* h, int layer_id, const void* d_in, const void* d_residual, void* d_out, int n,
                     void* stream);
+/* Same, for layers with a second input (in2_buf >= 0): d_in2 = that input in NHWC bf16. */
+int phdfx_run_layer2(phdfx_t* h, int layer_id, const void* d_in, const void* d_in2, const void* d_residual,
+                     void* d_out, int n, void* stream);
 
 int phdfx_layer_count(const phdfx_t* h);
 int phdfx_layer_info(const phdfx_t* h, int layer_id, phdfx_layer_desc* out);

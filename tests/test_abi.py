@@ -36,9 +36,9 @@ def test_version(lib, repo_root):
 
 
 def test_layer_desc_layout_matches_header():
-    # 14 x int32 + 2 x int64, no padding surprises
-    assert C.sizeof(_lib.LayerDesc) == 14 * 4 + 2 * 8
-    assert _lib.LayerDesc.w_off.offset == 56 and _lib.LayerDesc.b_off.offset == 64
+    # 18 x int32 + 2 x int64, no padding surprises
+    assert C.sizeof(_lib.LayerDesc) == 18 * 4 + 2 * 8
+    assert _lib.LayerDesc.w_off.offset == 72 and _lib.LayerDesc.b_off.offset == 80
 
 
 def test_geometry_constants_match_header(repo_root):

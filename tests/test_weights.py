@@ -32,21 +32,23 @@ def test_fold_is_exact_in_fp32(backbone):
 
 def test_plan_structure(plan, backbone):
     kinds = [l.kind for l in plan.layers]
-    assert kinds[0] == 3 and kinds.count(0) == 52  # fused stem+maxpool, 52 bottleneck convs
-    assert len(plan.layers) == 53 and plan.names[-1] == "layer4.2.conv3"
-    unfused = phdfx.build_plan(backbone, fuse_stem_pool=False)
+    assert kinds[0] == 3 and kinds.count(0) == 48  # fused stem+maxpool, 48 launches for the 52 bottleneck convs
+    assert len(plan.layers) == 49 and plan.names[-1] == "layer4.2.conv3"
+    assert sum(1 for l in plan.layers if l.in2_buf >= 0) == 4  # down-sample branches folded into conv3
+    unfused = phdfx.build_plan(backbone, fuse_stem_pool=False, fuse_downsample=False)
     assert [l.kind for l in unfused.layers[:2]] == [1, 2] and len(unfused.layers) == 54
+    assert sum(1 for l in unfused.layers if l.res_buf >= 0) == 16
+    assert sum(1 for n, l in zip(unfused.names, unfused.layers) if n.endswith("downsample") and l.relu == 0) == 4
     assert sum(l.gap for l in plan.layers) == 1 and plan.layers[-1].gap == 1
-    # 16 conv3 with residual, 4 downsample without relu
-    assert sum(1 for l in plan.layers if l.res_buf >= 0) == 16
-    assert sum(1 for n, l in zip(plan.names, plan.layers) if n.endswith("downsample") and l.relu == 0) == 4
+    # 12 conv3 with an identity residual; the 4 first-block conv3 carry the down-sample branch as a second source
+    assert sum(1 for l in plan.layers if l.res_buf >= 0) == 12
     # MAC count per frame: 4 087 136 256 including the stem
     macs = 0
     for l in plan.layers:
         if l.kind == 2:
             continue
         ho = (l.hin + 2 * l.pad - l.r) // l.stride + 1
-        macs += ho * ho * l.cout * l.cin * l.r * l.s
+        macs += ho * ho * l.cout * (l.cin * l.r * l.s + (l.cin2 if l.in2_buf >= 0 else 0))
     assert macs == 4_087_136_256
     # no layer writes a buffer it reads
     for l in plan.layers:
@@ -68,6 +70,8 @@ def test_dataflow_is_consistent(plan):
             ho = 56
         if l.res_buf >= 0:
             assert shape[l.res_buf] == (ho, l.cout), name
+        if l.in2_buf >= 0:
+            assert shape[l.in2_buf] == (l.hin2, l.cin2) and (l.hin2 - 1) // l.stride2 + 1 == ho, name
         shape[l.out_buf] = (ho, l.cout)
 
 
@@ -107,6 +111,17 @@ def test_pack_stem_pool_layout():
 
 def test_packed_weights_reproduce_the_network(backbone, plan):
     """Unpack layer2.0.conv2 from the blob and check it against the module (closes the loop pack -> offsets)."""
+    # fused conv3 + down-sample: weights [cout][width | cin], bias b3 + bd
+    j = plan.names.index("layer2.0.conv3+downsample")
+    lf = plan.layers[j]
+    kf = lf.cin + lf.cin2
+    wf = plan.weights[lf.w_off:lf.w_off + lf.cout * kf].to(torch.float32).reshape(lf.cout, kf)
+    blk0 = backbone[5][0]
+    w3, b3 = phdfx.fold_conv_bn(blk0.conv3, blk0.bn3)
+    wd, bd = phdfx.fold_conv_bn(blk0.downsample[0], blk0.downsample[1])
+    assert torch.equal(wf[:, :lf.cin], w3.reshape(lf.cout, -1).to(torch.bfloat16).to(torch.float32))
+    assert torch.equal(wf[:, lf.cin:], wd.reshape(lf.cout, -1).to(torch.bfloat16).to(torch.float32))
+    assert torch.equal(plan.bias[lf.b_off:lf.b_off + lf.cout], b3 + bd)
     i = plan.names.index("layer2.0.conv2")
     l = plan.layers[i]
     k = l.r * l.s * l.cin

@@ -48,14 +48,21 @@ def main():
         w_bytes = 0 if L.kind == 2 else (L.r * L.s * L.cin * L.cout * 2)
         macs = 0 if L.kind == 2 else n * ho * ho * L.cout * L.cin * L.r * L.s
         alg_bytes = in_bytes + out_bytes + (res.numel() * 2 if res is not None else 0) + w_bytes
-        eng.run_layer(i, x, res)
+        x2 = None
+        if L.in2_buf >= 0:
+            x2 = torch.randn(n, L.hin2, L.hin2, L.cin2, device="cuda", generator=g).to(torch.bfloat16)
+            in_bytes += x2.numel() * 2
+            w_bytes += L.cin2 * L.cout * 2
+            macs += n * ho * ho * L.cout * L.cin2
+            alg_bytes = in_bytes + out_bytes + w_bytes
+        eng.run_layer(i, x, res, x2)
         torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            eng.run_layer(i, x, res)
+            eng.run_layer(i, x, res, x2)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -71,7 +78,7 @@ def main():
                      "frac_hbm": round(gbs / pk["hbm_gbs"], 3), "ideal_ms": round(max(t_tensor, t_hbm), 4),
                      "bound": "tensor" if t_tensor > t_hbm else "hbm",
                      "eff_vs_roofline": round(max(t_tensor, t_hbm) / ms, 3)})
-        del x, res
+        del x, res, x2
     out = {"batch": n, "reps": reps, "sum_ms": tot_ms, "sum_ideal_ms": sum(r["ideal_ms"] for r in rows),
            "peaks": {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops_burst": pk["bf16_tflops"]}, "layers": rows}
     print(json.dumps(out, indent=1))

@@ -40,8 +40,9 @@ def main():
                 x = torch.randn(n, L.hin, L.win, L.cin, device="cuda", generator=g).to(torch.bfloat16)
             ho = (L.hin + 2 * L.pad - L.r) // L.stride + 1
             res = torch.randn(n, ho, ho, L.cout, device="cuda", generator=g).to(torch.bfloat16) if L.res_buf >= 0 else None
+            x2 = torch.randn(n, L.hin2, L.hin2, L.cin2, device="cuda", generator=g).to(torch.bfloat16) if L.in2_buf >= 0 else None
             for _ in range(2):
-                eng.run_layer(i, x, res)
+                eng.run_layer(i, x, res, x2)
             torch.cuda.synchronize()
             print("layer", i, eng.plan.names[i], "done")
 

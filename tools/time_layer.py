@@ -16,11 +16,12 @@ else:
 ho = (L.hin + 2 * L.pad - L.r) // L.stride + 1
 res = torch.randn(n, ho, ho, L.cout, device="cuda", generator=g).to(torch.bfloat16) if L.res_buf >= 0 else None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-eng.run_layer(i, x, res); torch.cuda.synchronize()
+x2 = torch.randn(n, L.hin2, L.hin2, L.cin2, device="cuda", generator=g).to(torch.bfloat16) if L.in2_buf >= 0 else None
+eng.run_layer(i, x, res, x2); torch.cuda.synchronize()
 ts = []
 for _ in range(reps):
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); eng.run_layer(i, x, res); e1.record(); torch.cuda.synchronize()
+    e0.record(); eng.run_layer(i, x, res, x2); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 print(f"layer {i} {eng.plan.names[i]} batch {n}: median {sorted(ts)[len(ts)//2]*1e3:.1f} us  min {min(ts)*1e3:.1f} us")
