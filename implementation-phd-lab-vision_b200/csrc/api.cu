@@ -12,6 +12,7 @@
 #include "../../include/phdfx.h"
 #include "conv_igemm_sm100.cuh"
 #include "conv_igemm_cg2_sm100.cuh"
+#include "bottleneck_chain_sm100.cuh"
 #include "elementwise_sm100.cuh"
 #include "stem_pool_sm100.cuh"
 
@@ -30,6 +31,15 @@ struct LayerMaps {
   bool valid = false;
 };
 
+// One fused launch of bottleneck_chain_kernel covering layers [first, first + span) of the execution list:
+// conv2 (3x3) -> conv3 (+ identity | fused down-sample) [-> the next block's conv1].
+struct ChainPlan {
+  int first = -1, span = 0;
+  bool has_ds = false;
+  int n1 = 0;  // output channels of the trailing conv1 (0 = none)
+  CUtensorMap mH, mX, mW2, mW3, mW1, mO, mR, mT;
+};
+
 }  // namespace
 
 struct phdfx {
@@ -45,6 +55,9 @@ struct phdfx {
   std::vector<void*> bufs;          // arena buffers by id
   std::vector<size_t> buf_bytes;    // per-frame bytes of each arena buffer
   int last_launches = 0;
+  bool use_chain = true;            // PHDFX_NO_CHAIN=1 at phdfx_create: keep layer1 on the per-conv kernels
+  std::vector<ChainPlan> chains;
+  std::vector<int> chain_at;        // per layer: index into `chains` of the chain STARTING there, else -1
 };
 
 namespace {
@@ -131,6 +144,7 @@ struct Geo {
 };
 
 bool g_use_cg2 = true;   // PHDFX_NO_CG2=1: keep the K-heavy layers on the 1-CTA kernel
+bool g_use_rev = true;   // PHDFX_NO_REV=1: every layer walks its tiles in ascending order (A/B measurements)
 bool g_use_halo = true;  // PHDFX_NO_HALO=1 (read at phdfx_create) falls back to the im2col path for A/B measurements
 
 Geo geometry(const phdfx_layer_desc& L) {
@@ -354,7 +368,7 @@ int launch_conv_cg2_t(phdfx_t* h, const LayerMaps& maps, const ConvParams& p, cu
 }
 
 int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bool has_res, void* out, int n,
-                cudaStream_t st) {
+                cudaStream_t st, int rev = 0) {
   const Geo g = geometry(L);
   ConvParams p{};
   p.Cout = L.cout;
@@ -375,6 +389,7 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bo
   p.halo_rt = g.halo_rt;
   p.kb_split = L.in2_buf >= 0 ? L.cin / 64 : g.num_kb;
   p.src2_stride = L.in2_buf >= 0 ? L.stride2 : 1;
+  p.rev = rev;
   if (g.mode == MODE_HALO)
     p.m_tiles = n * (g.P / g.halo_rt);
   else if (g.mode == MODE_STEM)
@@ -405,6 +420,107 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bo
       if (g.bn == 128) return launch_conv_t<128, MODE_IM2COL>(h, maps, p, st);
       return launch_conv_t<256, MODE_IM2COL>(h, maps, p, st);
   }
+}
+
+
+// ---- layer1 bottleneck chain (bottleneck_chain_sm100.cuh) ----------------------------------------------------------
+bool is_chain_conv2(const phdfx_layer_desc& L) {
+  return L.kind == PHDFX_CONV && L.r == 3 && L.s == 3 && L.stride == 1 && L.pad == 1 && L.hin == kChW &&
+         L.win == kChW && L.cin == 64 && L.cout == 64 && L.relu && L.res_buf < 0 && L.in2_buf < 0 && !L.gap;
+}
+bool is_chain_conv3(const phdfx_layer_desc& L, const phdfx_layer_desc& prev) {
+  if (!(L.kind == PHDFX_CONV && L.r == 1 && L.s == 1 && L.stride == 1 && L.pad == 0 && L.hin == kChW &&
+        L.win == kChW && L.cin == 64 && L.cout == 256 && L.relu && !L.gap && L.in_buf == prev.out_buf))
+    return false;
+  const bool ds = L.in2_buf >= 0 && L.cin2 == 64 && L.stride2 == 1 && L.hin2 == kChW && L.res_buf < 0;
+  const bool id = L.in2_buf < 0 && L.res_buf >= 0;
+  return (ds || id) && L.out_buf != prev.in_buf;
+}
+bool is_chain_conv1n(const phdfx_layer_desc& L, const phdfx_layer_desc& c3, const phdfx_layer_desc& c2) {
+  return L.kind == PHDFX_CONV && L.r == 1 && L.s == 1 && L.stride == 1 && L.pad == 0 && L.hin == kChW &&
+         L.win == kChW && L.cin == 256 && (L.cout == 64 || L.cout == 128) && L.relu && !L.gap && L.res_buf < 0 &&
+         L.in2_buf < 0 && L.in_buf == c3.out_buf && L.out_buf != c2.in_buf && L.out_buf != c3.res_buf &&
+         L.out_buf != c3.out_buf;
+}
+
+// how many layers starting at `i` run as one chain launch (0 = none)
+int chain_span_at(const std::vector<phdfx_layer_desc>& Ls, size_t i) {
+  if (i + 1 >= Ls.size() || !is_chain_conv2(Ls[i]) || !is_chain_conv3(Ls[i + 1], Ls[i])) return 0;
+  const bool ds = Ls[i + 1].in2_buf >= 0;
+  if (!ds && i + 2 < Ls.size() && is_chain_conv1n(Ls[i + 2], Ls[i + 1], Ls[i])) return 3;
+  return 2;
+}
+
+int build_chain_maps(phdfx_t* h, const phdfx_layer_desc& c2, const phdfx_layer_desc& c3, const phdfx_layer_desc* c1,
+                     const void* t1, const void* x, const void* res, void* out, void* t1n, int frames,
+                     ChainPlan* cp) {
+  cp->has_ds = c3.in2_buf >= 0;
+  cp->n1 = c1 ? c1->cout : 0;
+  memset(&cp->mX, 0, sizeof(CUtensorMap));
+  memset(&cp->mW1, 0, sizeof(CUtensorMap));
+  memset(&cp->mT, 0, sizeof(CUtensorMap));
+  memset(&cp->mR, 0, sizeof(CUtensorMap));
+  if (cp->has_ds ? (x == nullptr) : (res == nullptr))
+    return fail(h, PHDFX_ERR_INVALID, "chain: missing %s input", cp->has_ds ? "down-sample source" : "residual");
+  const cuuint64_t W = kChW, F = static_cast<cuuint64_t>(frames);
+  auto act4 = [&](CUtensorMap* m, const void* base, cuuint64_t ch, cuuint32_t rows, const char* what) {
+    cuuint64_t dims[4] = {ch, W, W, F};
+    cuuint64_t str[3] = {ch * 2, ch * 2 * W, ch * 2 * W * W};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(kChWP), rows, 1};
+    return encode_tiled(h, m, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
+  };
+  auto w2d = [&](CUtensorMap* m, const void* base, cuuint64_t K, cuuint64_t rows, cuuint32_t box_rows, const char* what) {
+    cuuint64_t dims[2] = {K, rows};
+    cuuint64_t str[1] = {K * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    return encode_tiled(h, m, base, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
+  };
+  if (int rc = act4(&cp->mH, t1, 64, kChRT + 2, "chain t1 patch")) return rc;
+  if (cp->has_ds)
+    if (int rc = act4(&cp->mX, x, 64, kChRT, "chain down-sample source")) return rc;
+  if (int rc = act4(&cp->mO, out, 256, kChRT, "chain out")) return rc;
+  if (!cp->has_ds)
+    if (int rc = act4(&cp->mR, res, 256, kChRT, "chain residual")) return rc;
+  if (c1)
+    if (int rc = act4(&cp->mT, t1n, c1->cout, kChRT, "chain next t1")) return rc;
+  if (int rc = w2d(&cp->mW2, h->d_weights + c2.w_off, 576, 64, 64, "chain W2")) return rc;
+  if (int rc = w2d(&cp->mW3, h->d_weights + c3.w_off, cp->has_ds ? 128 : 64, 256, 256, "chain W3")) return rc;
+  if (c1)
+    if (int rc = w2d(&cp->mW1, h->d_weights + c1->w_off, 256, c1->cout, 64, "chain W1n")) return rc;
+  return 0;
+}
+
+template <bool HAS_DS, int N1>
+int launch_chain_t(phdfx_t* h, const ChainPlan& cp, const ChainParams& p, cudaStream_t st) {
+  using Cfg = ChainCfg<HAS_DS, N1>;
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(bottleneck_chain_kernel<HAS_DS, N1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+    attr_set[h->device & 63] = true;
+  }
+  const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
+  CUDA_TRY(h, launch_pdl(bottleneck_chain_kernel<HAS_DS, N1>, dim3(grid), dim3(kChainThreads), Cfg::SMEM_BYTES, st,
+                         cp.mH, cp.mX, cp.mW2, cp.mW3, cp.mW1, cp.mO, cp.mR, cp.mT, p));
+  h->last_launches++;
+  return 0;
+}
+
+int launch_chain(phdfx_t* h, const ChainPlan& cp, int n, cudaStream_t st, int rev, long long* trace = nullptr) {
+  const auto& c2 = h->layers[cp.first];
+  const auto& c3 = h->layers[cp.first + 1];
+  ChainParams p{};
+  p.n_frames = n;
+  p.num_tiles = n * kChTilesPerFrame;
+  p.rev = rev;
+  p.bias2 = h->d_bias + c2.b_off;
+  p.bias3 = h->d_bias + c3.b_off;
+  p.bias1n = cp.n1 ? h->d_bias + h->layers[cp.first + 2].b_off : nullptr;
+  p.trace = trace;
+  if (cp.has_ds) return launch_chain_t<true, 0>(h, cp, p, st);
+  if (cp.n1 == 64) return launch_chain_t<false, 64>(h, cp, p, st);
+  if (cp.n1 == 128) return launch_chain_t<false, 128>(h, cp, p, st);
+  return launch_chain_t<false, 0>(h, cp, p, st);
 }
 
 // Fused stem + max-pool (stem_pool_sm100.cuh).  `out` receives [n][56][56][64] bf16.
@@ -466,6 +582,8 @@ void free_device_state(phdfx_t* h) {
   h->d_bias = nullptr;
   h->layers.clear();
   h->maps.clear();
+  h->chains.clear();
+  h->chain_at.clear();
 }
 
 int grid_1d(phdfx_t* h, long long total, int threads) {
@@ -488,6 +606,7 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   if (max_frames < 1) return fail(nullptr, PHDFX_ERR_INVALID, "max_frames must be >= 1");
   if (const char* e = getenv("PHDFX_NO_HALO")) g_use_halo = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_CG2")) g_use_cg2 = !(e[0] == '1');
+  if (const char* e = getenv("PHDFX_NO_REV")) g_use_rev = !(e[0] == '1');
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -505,6 +624,7 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   h->device = device_ordinal;
   h->max_frames = max_frames;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("PHDFX_NO_CHAIN")) h->use_chain = !(e[0] == '1');
   if (int rc = resolve_driver(h)) {
     delete h;
     return rc;
@@ -592,6 +712,30 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
                             h->max_frames, &h->maps[i]))
       return rc;
   }
+  // fused spans: layer1's conv2 -> conv3 [-> next conv1] run as one bottleneck_chain_kernel launch in phdfx_forward
+  h->chain_at.assign(n_layers, -1);
+  if (h->use_chain) {
+    for (int i = 0; i < n_layers;) {
+      const int span = chain_span_at(h->layers, static_cast<size_t>(i));
+      if (span == 0) {
+        ++i;
+        continue;
+      }
+      const auto& c2 = h->layers[i];
+      const auto& c3 = h->layers[i + 1];
+      const phdfx_layer_desc* c1 = span == 3 ? &h->layers[i + 2] : nullptr;
+      ChainPlan cp;
+      cp.first = i;
+      cp.span = span;
+      if (int rc = build_chain_maps(h, c2, c3, c1, h->bufs[c2.in_buf], c3.in2_buf >= 0 ? h->bufs[c3.in2_buf] : nullptr,
+                                    c3.res_buf >= 0 ? h->bufs[c3.res_buf] : nullptr, h->bufs[c3.out_buf],
+                                    c1 ? h->bufs[c1->out_buf] : nullptr, h->max_frames, &cp))
+        return rc;
+      h->chain_at[i] = static_cast<int>(h->chains.size());
+      h->chains.push_back(cp);
+      i += span;
+    }
+  }
   CUDA_TRY(h, cudaDeviceSynchronize());
   return 0;
 }
@@ -634,11 +778,20 @@ int phdfx_nchw_f32_to_nhwc_bf16(phdfx_t* h, const float* d_x, int n, void* d_out
 static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cudaStream_t st) {
   if (!d_feats) return fail(h, PHDFX_ERR_INVALID, "phdfx_forward: null d_feats");
   bool wrote_feats = false;
-  for (size_t i = 0; i < h->layers.size(); ++i) {
+  int launch_no = 0;
+  for (size_t i = 0; i < h->layers.size(); ++i, ++launch_no) {
     const auto& L = h->layers[i];
     const void* in = h->bufs[L.in_buf];
     void* out = L.gap ? static_cast<void*>(d_feats) : h->bufs[L.out_buf];
     const void* res = L.res_buf >= 0 ? h->bufs[L.res_buf] : nullptr;
+    // serpentine: odd launches walk their tiles backwards, i.e. start where the previous launch ended
+    const int rev = (g_use_rev && (launch_no & 1)) ? 1 : 0;
+    if (h->chain_at[i] >= 0) {
+      const ChainPlan& cp = h->chains[h->chain_at[i]];
+      if (int rc = launch_chain(h, cp, n, st, rev)) return rc;
+      i += cp.span - 1;
+      continue;
+    }
     if (L.kind == PHDFX_MAXPOOL) {
       if (int rc = launch_maxpool(h, L, in, out, n, st)) return rc;
       continue;
@@ -654,9 +807,9 @@ static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cud
       LayerMaps tmp;
       if (int rc = build_maps(h, L, d_in, nullptr, res, L.gap ? nullptr : out, n, &tmp)) return rc;
       tmp.o = h->maps[i].o;
-      if (int rc = launch_conv(h, L, tmp, res != nullptr, out, n, st)) return rc;
+      if (int rc = launch_conv(h, L, tmp, res != nullptr, out, n, st, rev)) return rc;
     } else {
-      if (int rc = launch_conv(h, L, h->maps[i], res != nullptr, out, n, st)) return rc;
+      if (int rc = launch_conv(h, L, h->maps[i], res != nullptr, out, n, st, rev)) return rc;
     }
     if (L.gap) wrote_feats = true;
   }
@@ -705,6 +858,54 @@ int phdfx_run_layer2(phdfx_t* h, int layer_id, const void* d_in, const void* d_i
 int phdfx_run_layer(phdfx_t* h, int layer_id, const void* d_in, const void* d_residual, void* d_out, int n,
                     void* stream) {
   return phdfx_run_layer2(h, layer_id, d_in, nullptr, d_residual, d_out, n, stream);
+}
+
+int phdfx_chain_span(const phdfx_t* h, int layer_id) {
+  if (!h || layer_id < 0 || layer_id >= static_cast<int>(h->chain_at.size()) || h->chain_at[layer_id] < 0) return 0;
+  return h->chains[h->chain_at[layer_id]].span;
+}
+
+int phdfx_run_chain(phdfx_t* h, int first_layer_id, const void* d_t1, const void* d_x_or_res, void* d_out,
+                    void* d_t1_next, int n, void* stream) {
+  if (int rc = check_ready(h, n)) return rc;
+  const int span = chain_span_at(h->layers, static_cast<size_t>(first_layer_id < 0 ? h->layers.size() : first_layer_id));
+  if (span == 0) return fail(h, PHDFX_ERR_INVALID, "no fusable conv2 -> conv3 [-> conv1] chain starts at layer %d", first_layer_id);
+  if (!d_t1 || !d_x_or_res || !d_out || (span == 3 && !d_t1_next))
+    return fail(h, PHDFX_ERR_INVALID, "phdfx_run_chain: null buffer");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  h->last_launches = 0;
+  const auto& c2 = h->layers[first_layer_id];
+  const auto& c3 = h->layers[first_layer_id + 1];
+  const phdfx_layer_desc* c1 = span == 3 ? &h->layers[first_layer_id + 2] : nullptr;
+  ChainPlan cp;
+  cp.first = first_layer_id;
+  cp.span = span;
+  const bool ds = c3.in2_buf >= 0;
+  if (int rc = build_chain_maps(h, c2, c3, c1, d_t1, ds ? d_x_or_res : nullptr, ds ? nullptr : d_x_or_res, d_out,
+                                d_t1_next, n, &cp))
+    return rc;
+  if (const char* path = getenv("PHDFX_CHAIN_TRACE")) {
+    // debug: clock64 timeline of CTA 0's pipeline events, appended to `path` (synchronises; never set in production)
+    long long* d_trace = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_trace, 32 * 32 * sizeof(long long)));
+    CUDA_TRY(h, cudaMemset(d_trace, 0, 32 * 32 * sizeof(long long)));
+    int rc = launch_chain(h, cp, n, static_cast<cudaStream_t>(stream), 0, d_trace);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    std::vector<long long> host(32 * 32);
+    CUDA_TRY(h, cudaMemcpy(host.data(), d_trace, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_trace);
+    if (FILE* f = fopen(path, "a")) {
+      fprintf(f, "chain first=%d span=%d n=%d\n", first_layer_id, span, n);
+      for (int k = 0; k < 32; ++k) {
+        fprintf(f, "%d", k);
+        for (int e = 0; e < 32; ++e) fprintf(f, " %lld", host[k * 32 + e]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    return rc;
+  }
+  return launch_chain(h, cp, n, static_cast<cudaStream_t>(stream), 0);
 }
 
 int phdfx_layer_count(const phdfx_t* h) { return h ? static_cast<int>(h->layers.size()) : 0; }

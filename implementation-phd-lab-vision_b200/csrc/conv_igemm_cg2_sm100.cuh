@@ -203,7 +203,8 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
-    for (int pt = pair; pt < num_ptiles; pt += num_pairs) {
+    for (int lp = pair; lp < num_ptiles; lp += num_pairs) {
+      const int pt = p.rev ? num_ptiles - 1 - lp : lp;
       const int m_pair = pt / p.n_tiles;
       const int n_blk = pt - m_pair * p.n_tiles;
       const int m_blk = 2 * m_pair + static_cast<int>(rank);
@@ -303,7 +304,8 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const int u = t - LOOK;
           const int b = u % NB;
           mbar_wait(&out_full[b], (u / NB) & 1);
-          const int pt = pair + (u / GROUPS) * num_pairs;
+          const int lp = pair + (u / GROUPS) * num_pairs;
+          const int pt = p.rev ? num_ptiles - 1 - lp : lp;
           const int g = u % GROUPS;
           const int m_pair = pt / p.n_tiles;
           const int n_blk = pt - m_pair * p.n_tiles;
@@ -324,7 +326,8 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     uint32_t acc_phase = 0;
     int it = 0;
     int jg = 0;
-    for (int pt = pair; pt < num_ptiles; pt += num_pairs, ++it) {
+    for (int lp = pair; lp < num_ptiles; lp += num_pairs, ++it) {
+      const int pt = p.rev ? num_ptiles - 1 - lp : lp;
       const int m_pair = pt / p.n_tiles;
       const int n_blk = pt - m_pair * p.n_tiles;
       const int n_base = n_blk * BN;

@@ -54,6 +54,8 @@ struct ConvParams {
   int kb_split;    // MODE_TILED with a second source (fused down-sample): K blocks [0, kb_split) come from mapA,
                    // [kb_split, num_kb) from mapA2; = num_kb when there is no second source
   int src2_stride; // second source: 1 = tiled 2-D map over its activation matrix, 2 = im2col map (1x1 stride 2)
+  int rev;         // 1: walk the tiles in descending order.  Consecutive layers alternate direction, so a layer starts
+                   // on the rows its predecessor wrote last — the part of the activation tensor still resident in L2
   const float* bias;  // [Cout] folded BN bias
   float* feats;       // MODE_GAP: [n_frames, Cout]
 };
@@ -185,7 +187,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           tma_load_2d_elect(&mapB, &full_bar[tap], smem + tap * Cfg::STAGE_BYTES, tap * 64, 0);
         }
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int lt = blockIdx.x; lt < num_tiles; lt += gridDim.x) {
+        const int tile = p.rev ? num_tiles - 1 - lt : lt;
         const int m_blk = tile / p.n_tiles;
         const int n_blk = tile - m_blk * p.n_tiles;
         // per-tile A coordinates
@@ -362,7 +365,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (MODE != MODE_GAP && t >= NB) tma_store_wait_read<NB - LOOK - 1>();  // store t-NB has left smem
           const int b = t % NB;
           if (p.has_res) {
-            const int tile = blockIdx.x + (t / GROUPS) * gridDim.x;
+            const int lt = blockIdx.x + (t / GROUPS) * gridDim.x;
+            const int tile = p.rev ? num_tiles - 1 - lt : lt;
             const int g = t % GROUPS;
             const int m_blk = tile / p.n_tiles;
             const int n_blk = tile - m_blk * p.n_tiles;
@@ -379,7 +383,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const int b = u % NB;
           mbar_wait(&out_full[b], (u / NB) & 1);
           if (MODE != MODE_GAP) {
-            const int tile = blockIdx.x + (u / GROUPS) * gridDim.x;
+            const int lt = blockIdx.x + (u / GROUPS) * gridDim.x;
+            const int tile = p.rev ? num_tiles - 1 - lt : lt;
             const int g = u % GROUPS;
             const int m_blk = tile / p.n_tiles;
             const int n_blk = tile - m_blk * p.n_tiles;
@@ -413,7 +418,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint32_t acc_phase = 0;
     int it = 0;
     int jg = 0;  // running group counter (matches the DMA thread's t / u)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int lt = blockIdx.x; lt < num_tiles; lt += gridDim.x, ++it) {
+      const int tile = p.rev ? num_tiles - 1 - lt : lt;
       const int m_blk = tile / p.n_tiles;
       const int n_blk = tile - m_blk * p.n_tiles;
       const int n_base = n_blk * BN;

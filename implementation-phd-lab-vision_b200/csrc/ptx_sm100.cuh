@@ -186,6 +186,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread (lane t <-> TMEM lane base+t).  Used to park a
+// bf16 tile (two K elements per column) in TMEM as the A operand of a later tcgen05.mma.
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- warp-uniform issue: every lane of the (converged) warp executes the statement, one elected lane performs it.
 // Keeping the surrounding control flow warp-uniform lets ptxas hold descriptors / coordinates in uniform registers
@@ -200,6 +211,19 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc,
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A operand in TENSOR MEMORY (128 lanes = GEMM rows, bf16 pairs along the columns: K = 16 is 8 columns), B in smem.
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // One K block = four (or two) K=16 MMAs issued back to back under ONE election; each step advances both descriptors'

@@ -24,6 +24,8 @@ EXPORTS = [
     "phdfx_extract_u8",
     "phdfx_run_layer",
     "phdfx_run_layer2",
+    "phdfx_chain_span",
+    "phdfx_run_chain",
     "phdfx_layer_count",
     "phdfx_layer_info",
     "phdfx_last_launch_count",
@@ -101,6 +103,10 @@ def load() -> C.CDLL:
     lib.phdfx_run_layer.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     lib.phdfx_run_layer2.restype = i32
     lib.phdfx_run_layer2.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
+    lib.phdfx_chain_span.restype = i32
+    lib.phdfx_chain_span.argtypes = [vp, i32]
+    lib.phdfx_run_chain.restype = i32
+    lib.phdfx_run_chain.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
     lib.phdfx_layer_count.restype = i32
     lib.phdfx_layer_count.argtypes = [vp]
     lib.phdfx_layer_info.restype = i32

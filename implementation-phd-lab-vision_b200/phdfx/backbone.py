@@ -207,6 +207,34 @@ class B200Backbone:
         return out
 
 
+    # ---- fused-span hook ---------------------------------------------------------------------------------------------
+    def chain_span(self, layer_id: int) -> int:
+        """Number of execution-list entries the fused launch starting at `layer_id` covers (0 = none starts there)."""
+        return int(self._lib.phdfx_chain_span(self._h, layer_id))
+
+    @torch.no_grad()
+    def run_chain(self, first_layer_id: int, t1: torch.Tensor, x_or_res: torch.Tensor):
+        """Run the fused layer1 chain that starts at conv2 = `first_layer_id` on explicit NHWC bf16 tensors:
+        t1 [n,56,56,64], x_or_res = down-sample source [n,56,56,64] or identity residual [n,56,56,256].
+        Returns (out [n,56,56,256], next block's t1 [n,56,56,cout] or None)."""
+        span = self.chain_span(first_layer_id)
+        if span == 0:
+            raise RuntimeError(f"no fused chain starts at layer {first_layer_id}")
+        self._check_dev(t1, "t1")
+        self._check_dev(x_or_res, "x_or_res")
+        n = t1.shape[0]
+        out = torch.empty(n, 56, 56, 256, device=self.device, dtype=torch.bfloat16)
+        t1n = None
+        if span == 3:
+            t1n = torch.empty(n, 56, 56, self.plan.layers[first_layer_id + 2].cout, device=self.device,
+                              dtype=torch.bfloat16)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.phdfx_run_chain(self._h, first_layer_id, t1.data_ptr(), x_or_res.data_ptr(),
+                                                 out.data_ptr(), t1n.data_ptr() if t1n is not None else None, n,
+                                                 self._stream()), self._h)
+        return out, t1n
+
+
 class ExtractGraph:
     """One whole step of the hot path (K1 + fused stem/max-pool + 52 convs) frozen into a CUDA graph.
 

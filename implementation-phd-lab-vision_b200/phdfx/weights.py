@@ -128,7 +128,11 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample
                            in_buf=1, out_buf=2))
         names.append("maxpool")
 
-    x_buf, o_buf = 2, 1  # block input / block output ping-pong; 3, 4, 5 = conv1 out, conv2 out, downsample out
+    # block input / block output ping-pong on 2 / 1; conv1 out (t1) and conv2 out (t2) alternate between 3 and 4 from
+    # block to block, so a block's t1 and the NEXT block's t1 never share a buffer — the fused layer1 chain
+    # (bottleneck_chain_sm100.cuh) reads the former (with halo rows of neighbouring tiles) while writing the latter;
+    # 5 = down-sample out (unfused plan only)
+    x_buf, o_buf = 2, 1
     h = 56
     n_blocks = sum(len(s) for s in stages)
     blk_i = 0
@@ -141,17 +145,18 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample
             width = blk.conv1.out_channels
             cout = blk.conv3.out_channels
             stride = blk.conv2.stride[0]
+            t1_buf, t2_buf = (3, 4) if blk_i % 2 == 1 else (4, 3)
             # conv1 1x1 + bn1 + relu (resnet.py:146-148)
             w, b = fold_conv_bn(blk.conv1, blk.bn1)
             w_off, b_off = add_weights(pack_conv(w), b)
-            layers.append(desc(cin=cin, cout=width, hin=h, win=h, relu=1, in_buf=x_buf, out_buf=3, w_off=w_off,
+            layers.append(desc(cin=cin, cout=width, hin=h, win=h, relu=1, in_buf=x_buf, out_buf=t1_buf, w_off=w_off,
                                b_off=b_off))
             names.append(name + ".conv1")
             # conv2 3x3 (stride lives here: v1.5, resnet.py:109-113) + bn2 + relu (:150-152)
             w, b = fold_conv_bn(blk.conv2, blk.bn2)
             w_off, b_off = add_weights(pack_conv(w), b)
             layers.append(desc(cin=width, cout=width, r=3, s=3, stride=stride, pad=1, hin=h, win=h, relu=1,
-                               in_buf=3, out_buf=4, w_off=w_off, b_off=b_off))
+                               in_buf=t1_buf, out_buf=t2_buf, w_off=w_off, b_off=b_off))
             names.append(name + ".conv2")
             ho = (h + 2 - 3) // stride + 1
             res_buf = x_buf
@@ -162,7 +167,7 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample
                 wd, bd = fold_conv_bn(dconv, dbn)
                 wcat = torch.cat([w3.reshape(cout, width), wd.reshape(cout, cin)], dim=1)  # [cout][width | cin]
                 w_off, b_off = add_weights(wcat.contiguous().to(torch.bfloat16).reshape(-1), b3 + bd)
-                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=4, out_buf=o_buf, res_buf=-1,
+                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=t2_buf, out_buf=o_buf, res_buf=-1,
                                    gap=1 if last else 0, in2_buf=x_buf, cin2=cin, stride2=dconv.stride[0], hin2=h,
                                    w_off=w_off, b_off=b_off))
                 names.append(name + ".conv3+downsample")
@@ -178,7 +183,7 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample
                     res_buf = 5
                 # conv3 1x1 + bn3 + residual + relu (:154-161); the last one also fuses avgpool (:278)
                 w_off, b_off = add_weights(pack_conv(w3), b3)
-                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=4, out_buf=o_buf,
+                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=t2_buf, out_buf=o_buf,
                                    res_buf=res_buf, gap=1 if last else 0, w_off=w_off, b_off=b_off))
                 names.append(name + ".conv3")
             x_buf, o_buf = o_buf, x_buf

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PHDFX_VERSION 100 /* major*100 + minor */
+#define PHDFX_VERSION 101 /* major*100 + minor */
 
 typedef struct phdfx phdfx_t;
 
@@ -108,6 +108,18 @@ int phdfx_run_layer(phdfx_t* h, int layer_id, const void* d_in, const void* d_re
 /* Same, for layers with a second input (in2_buf >= 0): d_in2 = that input in NHWC bf16. */
 int phdfx_run_layer2(phdfx_t* h, int layer_id, const void* d_in, const void* d_in2, const void* d_residual,
                      void* d_out, int n, void* stream);
+
+/* Fused spans.  phdfx_forward runs layer1's  conv2 (3x3) -> conv3 (+ identity | fused down-sample) [-> the next
+ * block's conv1]  (resnet.py:150-161 and the following :146-148) as ONE launch (bottleneck_chain_sm100.cuh) whenever the
+ * execution list has that pattern with distinct buffers; PHDFX_NO_CHAIN=1 in the environment at phdfx_create keeps
+ * the per-conv kernels.  phdfx_chain_span: number of list entries the launch starting at layer_id covers (0 = no fused
+ * launch starts there).  phdfx_run_chain: that launch on caller buffers (parity tests / per-kernel benchmark):
+ * d_t1 = conv2's input [n][56][56][64]; d_x_or_res = the down-sample source [n][56][56][64] when conv3 carries a
+ * second input, else the identity residual [n][56][56][256]; d_out = block output [n][56][56][256]; d_t1_next = the
+ * trailing conv1's output [n][56][56][cout] (NULL when the span is 2).  All NHWC bf16. */
+int phdfx_chain_span(const phdfx_t* h, int layer_id);
+int phdfx_run_chain(phdfx_t* h, int first_layer_id, const void* d_t1, const void* d_x_or_res, void* d_out,
+                    void* d_t1_next, int n, void* stream);
 
 int phdfx_layer_count(const phdfx_t* h);
 int phdfx_layer_info(const phdfx_t* h, int layer_id, phdfx_layer_desc* out);

@@ -179,6 +179,77 @@ def test_every_layer_shape_vs_fp32_torch(eng, backbone, n):
     assert checked >= 24
 
 
+def _chain_reference(eng, mods, first, t1, x_or_res):
+    """fp32 PyTorch restatement of one fused chain on the same bf16-rounded operands, rounding to bf16 exactly where the
+    kernel does (t2, the block output)."""
+    names, layers = eng.plan.names, eng.plan.layers
+    span = eng.chain_span(first)
+
+    def wb(name):
+        conv, bn = mods[name]
+        w, b = phdfx.fold_conv_bn(conv, bn)
+        return w.to(torch.bfloat16).float().cuda(), b.cuda()
+
+    nchw = lambda t: t.float().permute(0, 3, 1, 2)
+    w2, b2 = wb(names[first])
+    t2 = torch.relu(F.conv2d(nchw(t1), w2, b2, padding=1)).to(torch.bfloat16).float()
+    n3 = names[first + 1]
+    w3, b3 = wb(n3.replace("+downsample", ""))
+    y = F.conv2d(t2, w3, b3)
+    if layers[first + 1].in2_buf >= 0:
+        wd, bd = wb(n3.replace("conv3+downsample", "downsample"))
+        y = y + F.conv2d(nchw(x_or_res), wd, bd)
+    else:
+        y = y + nchw(x_or_res)
+    out = torch.relu(y)
+    t1n = None
+    if span == 3:
+        w1, b1 = wb(names[first + 2])
+        t1n = torch.relu(F.conv2d(out.to(torch.bfloat16).float(), w1, b1)).permute(0, 2, 3, 1)
+    return out.permute(0, 2, 3, 1), t1n
+
+
+@pytest.mark.parametrize("n", [1, 3, 11])
+def test_layer1_chain_kernel_vs_fp32_torch(eng, backbone, n):
+    """bottleneck_chain_kernel (conv2 -> conv3 [+identity | +down-sample] [-> next conv1] in one launch), every
+    variant the plan uses, on explicit tensors.  n = 11 gives each CTA of a 148-SM grid several tiles (the software
+    pipeline across tiles), n = 1 fewer tiles than SMs."""
+    mods = _layer_modules(backbone)
+    g = torch.Generator(device="cuda").manual_seed(300 + n)
+    firsts = [i for i in range(len(eng.plan.layers)) if eng.chain_span(i) > 0]
+    assert [eng.chain_span(i) for i in firsts] == [2, 3, 3]
+    for first in firsts:
+        L3 = eng.plan.layers[first + 1]
+        t1 = torch.relu(torch.randn(n, 56, 56, 64, device="cuda", generator=g)).to(torch.bfloat16)
+        c = 64 if L3.in2_buf >= 0 else 256
+        xr = torch.randn(n, 56, 56, c, device="cuda", generator=g).to(torch.bfloat16)
+        out, t1n = eng.run_chain(first, t1, xr)
+        ref_out, ref_t1n = _chain_reference(eng, mods, first, t1, xr)
+        err = (out.float() - ref_out).abs().max().item() / ref_out.abs().max().item()
+        assert err < 6e-3, f"{eng.plan.names[first]}: block output normalised error {err}"
+        if ref_t1n is not None:
+            err = (t1n.float() - ref_t1n).abs().max().item() / ref_t1n.abs().max().item()
+            assert err < 1e-2, f"{eng.plan.names[first + 2]}: next t1 normalised error {err}"
+
+
+def test_layer1_chain_is_bit_identical_to_per_conv_kernels(backbone):
+    """The fused chain performs the same MMAs in the same order with the same roundings as the three kernels it
+    replaces: features are bit-identical with PHDFX_NO_CHAIN=1, at a batch that gives every CTA several tiles."""
+    frames = torch.from_numpy(R.seeded_frames(24, 224, 224, 41)).cuda()
+    fused = phdfx.B200Backbone(backbone, device=0, max_frames=24)
+    os.environ["PHDFX_NO_CHAIN"] = "1"
+    try:
+        plain = phdfx.B200Backbone(backbone, device=0, max_frames=24)
+    finally:
+        del os.environ["PHDFX_NO_CHAIN"]
+    a = fused.extract_u8(frames, None)
+    b = plain.extract_u8(frames, None)
+    assert fused.launches == 45 and plain.launches == 50
+    assert torch.equal(a, b)
+    fused.close()
+    plain.close()
+
+
 @pytest.mark.parametrize("n", [1, 3])
 def test_unfused_stem_and_maxpool_kernels(backbone, n):
     """The separate implicit-GEMM stem and max-pool kernels (fuse_stem_pool=False) and the fused kernel agree
@@ -188,12 +259,12 @@ def test_unfused_stem_and_maxpool_kernels(backbone, n):
     frames = torch.from_numpy(R.seeded_frames(n, 224, 224, 31)).cuda()
     a = fused.extract_u8(frames, None)
     b = unfused.extract_u8(frames, None)
-    assert fused.launches == 50 and unfused.launches == 51
+    assert fused.launches == 45 and unfused.launches == 46
     assert torch.equal(a, b)
     # separate down-sample launches + residual add (rounds the branch to bf16 first): same features within bf16 noise
     plain = phdfx.B200Backbone(backbone, device=0, max_frames=4, fuse_downsample=False)
     c = plain.extract_u8(frames, None)
-    assert plain.launches == 54
+    assert plain.launches == 50
     err, cos = frame_errors(c.cpu().numpy(), a.cpu().numpy())
     assert err.max() < 1e-2 and cos.min() > 0.9999
     plain.close()
@@ -320,7 +391,7 @@ def test_cuda_graph_replay_is_bit_identical(eng):
     assert torch.equal(g.replay(), eng.extract_u8(frames[:10].contiguous(), boxes[:10].contiguous()))
     buf.copy_(frames[10:])
     assert torch.equal(g.replay(), eng.extract_u8(frames[10:].contiguous(), boxes[10:].contiguous()))
-    assert g.launches == 50
+    assert g.launches == 45
 
 
 def test_errors_are_loud(eng):
@@ -345,7 +416,9 @@ def test_full_batch_256_properties():
     e = phdfx.B200Backbone(bb, device=0, max_frames=256)
     frames = torch.from_numpy(R.seeded_frames(256, 224, 224, 13)).cuda()
     big = e.extract_u8(frames, None)
-    assert e.launches == 50  # K1 + fused stem/maxpool + 48 conv launches (4 down-samples ride in conv3), all ours
+    # K1 + fused stem/maxpool + 43 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 -> next conv1
+    # chains are one launch each), all ours
+    assert e.launches == 45
     small = torch.cat([e.extract_u8(frames[i:i + 37].contiguous(), None) for i in range(0, 256, 37)])
     assert torch.equal(big, small)
     assert torch.isfinite(big).all()
