@@ -447,7 +447,9 @@ bool is_chain_conv1n(const phdfx_layer_desc& L, const phdfx_layer_desc& c3, cons
 int chain_span_at(const std::vector<phdfx_layer_desc>& Ls, size_t i) {
   if (i + 1 >= Ls.size() || !is_chain_conv2(Ls[i]) || !is_chain_conv3(Ls[i + 1], Ls[i])) return 0;
   const bool ds = Ls[i + 1].in2_buf >= 0;
-  if (!ds && i + 2 < Ls.size() && is_chain_conv1n(Ls[i + 2], Ls[i + 1], Ls[i])) return 3;
+  if (i + 2 < Ls.size() && is_chain_conv1n(Ls[i + 2], Ls[i + 1], Ls[i]) && !(ds && Ls[i + 2].cout != 64) &&
+      !(ds && Ls[i + 2].out_buf == Ls[i + 1].in2_buf))
+    return 3;
   return 2;
 }
 
@@ -517,7 +519,7 @@ int launch_chain(phdfx_t* h, const ChainPlan& cp, int n, cudaStream_t st, int re
   p.bias3 = h->d_bias + c3.b_off;
   p.bias1n = cp.n1 ? h->d_bias + h->layers[cp.first + 2].b_off : nullptr;
   p.trace = trace;
-  if (cp.has_ds) return launch_chain_t<true, 0>(h, cp, p, st);
+  if (cp.has_ds) return cp.n1 == 64 ? launch_chain_t<true, 64>(h, cp, p, st) : launch_chain_t<true, 0>(h, cp, p, st);
   if (cp.n1 == 64) return launch_chain_t<false, 64>(h, cp, p, st);
   if (cp.n1 == 128) return launch_chain_t<false, 128>(h, cp, p, st);
   return launch_chain_t<false, 0>(h, cp, p, st);

@@ -84,7 +84,7 @@ bottleneck_chain_kernel(const __grid_constant__ CUtensorMap mapH,   // t1 [n][56
   static_assert(D >= 4, "weight ring too shallow");
   static_assert(Cfg::SMEM_BYTES <= Cfg::SMEM_MAX, "shared memory budget exceeded");
   static_assert(N1 == 0 || N1 == 64 || N1 == 128, "next conv1 width");
-  static_assert(!(HAS_DS && N1 > 0), "the down-sample variant has no room for the next conv1");
+  static_assert(!(HAS_DS && N1 > 64), "the down-sample variant is only paired with a 64-wide next conv1");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
