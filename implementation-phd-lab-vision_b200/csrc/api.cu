@@ -37,6 +37,7 @@ struct ChainPlan {
   int first = -1, span = 0;
   bool has_ds = false;
   int n1 = 0;  // output channels of the trailing conv1 (0 = none)
+  int w = 56;  // spatial size: 56 (layer1) or 28 (layer2)
   CUtensorMap mH, mX, mW2, mW3, mW1, mO, mR, mT;
 };
 
@@ -423,33 +424,33 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bo
 }
 
 
-// ---- layer1 bottleneck chain (bottleneck_chain_sm100.cuh) ----------------------------------------------------------
+// ---- bottleneck chain (bottleneck_chain_sm100.cuh): layer1 (56x56, width 64) and layer2 (28x28, width 128) ---------
 bool is_chain_conv2(const phdfx_layer_desc& L) {
-  return L.kind == PHDFX_CONV && L.r == 3 && L.s == 3 && L.stride == 1 && L.pad == 1 && L.hin == kChW &&
-         L.win == kChW && L.cin == 64 && L.cout == 64 && L.relu && L.res_buf < 0 && L.in2_buf < 0 && !L.gap;
+  const bool geo = (L.hin == 56 && L.cin == 64) || (L.hin == 28 && L.cin == 128);
+  return L.kind == PHDFX_CONV && L.r == 3 && L.s == 3 && L.stride == 1 && L.pad == 1 && geo && L.win == L.hin &&
+         L.cout == L.cin && L.relu && L.res_buf < 0 && L.in2_buf < 0 && !L.gap;
 }
 bool is_chain_conv3(const phdfx_layer_desc& L, const phdfx_layer_desc& prev) {
-  if (!(L.kind == PHDFX_CONV && L.r == 1 && L.s == 1 && L.stride == 1 && L.pad == 0 && L.hin == kChW &&
-        L.win == kChW && L.cin == 64 && L.cout == 256 && L.relu && !L.gap && L.in_buf == prev.out_buf))
+  if (!(L.kind == PHDFX_CONV && L.r == 1 && L.s == 1 && L.stride == 1 && L.pad == 0 && L.hin == prev.hin &&
+        L.win == prev.hin && L.cin == prev.cout && L.cout == 4 * prev.cout && L.relu && !L.gap &&
+        L.in_buf == prev.out_buf))
     return false;
-  const bool ds = L.in2_buf >= 0 && L.cin2 == 64 && L.stride2 == 1 && L.hin2 == kChW && L.res_buf < 0;
+  const bool ds = L.in2_buf >= 0 && L.cin2 == 64 && L.stride2 == 1 && L.hin2 == 56 && L.hin == 56 && L.res_buf < 0;
   const bool id = L.in2_buf < 0 && L.res_buf >= 0;
   return (ds || id) && L.out_buf != prev.in_buf;
 }
 bool is_chain_conv1n(const phdfx_layer_desc& L, const phdfx_layer_desc& c3, const phdfx_layer_desc& c2) {
-  return L.kind == PHDFX_CONV && L.r == 1 && L.s == 1 && L.stride == 1 && L.pad == 0 && L.hin == kChW &&
-         L.win == kChW && L.cin == 256 && (L.cout == 64 || L.cout == 128) && L.relu && !L.gap && L.res_buf < 0 &&
-         L.in2_buf < 0 && L.in_buf == c3.out_buf && L.out_buf != c2.in_buf && L.out_buf != c3.res_buf &&
-         L.out_buf != c3.out_buf;
+  return L.kind == PHDFX_CONV && L.r == 1 && L.s == 1 && L.stride == 1 && L.pad == 0 && L.hin == 56 &&
+         L.win == 56 && c3.hin == 56 && L.cin == 256 && (L.cout == 64 || L.cout == 128) && L.relu && !L.gap &&
+         L.res_buf < 0 && L.in2_buf < 0 && L.in_buf == c3.out_buf && L.out_buf != c2.in_buf &&
+         L.out_buf != c3.res_buf && L.out_buf != c3.out_buf && L.out_buf != c3.in2_buf;
 }
 
 // how many layers starting at `i` run as one chain launch (0 = none)
 int chain_span_at(const std::vector<phdfx_layer_desc>& Ls, size_t i) {
   if (i + 1 >= Ls.size() || !is_chain_conv2(Ls[i]) || !is_chain_conv3(Ls[i + 1], Ls[i])) return 0;
   const bool ds = Ls[i + 1].in2_buf >= 0;
-  if (i + 2 < Ls.size() && is_chain_conv1n(Ls[i + 2], Ls[i + 1], Ls[i]) && !(ds && Ls[i + 2].cout != 64) &&
-      !(ds && Ls[i + 2].out_buf == Ls[i + 1].in2_buf))
-    return 3;
+  if (i + 2 < Ls.size() && is_chain_conv1n(Ls[i + 2], Ls[i + 1], Ls[i]) && !(ds && Ls[i + 2].cout != 64)) return 3;
   return 2;
 }
 
@@ -458,17 +459,20 @@ int build_chain_maps(phdfx_t* h, const phdfx_layer_desc& c2, const phdfx_layer_d
                      ChainPlan* cp) {
   cp->has_ds = c3.in2_buf >= 0;
   cp->n1 = c1 ? c1->cout : 0;
+  cp->w = c2.hin;
   memset(&cp->mX, 0, sizeof(CUtensorMap));
   memset(&cp->mW1, 0, sizeof(CUtensorMap));
   memset(&cp->mT, 0, sizeof(CUtensorMap));
   memset(&cp->mR, 0, sizeof(CUtensorMap));
   if (cp->has_ds ? (x == nullptr) : (res == nullptr))
     return fail(h, PHDFX_ERR_INVALID, "chain: missing %s input", cp->has_ds ? "down-sample source" : "residual");
-  const cuuint64_t W = kChW, F = static_cast<cuuint64_t>(frames);
+  const cuuint64_t W = c2.hin, F = static_cast<cuuint64_t>(frames);
+  const cuuint32_t rt = c2.hin == 56 ? 2 : 4;
+  const cuuint64_t C2 = c2.cout, N3 = c3.cout;
   auto act4 = [&](CUtensorMap* m, const void* base, cuuint64_t ch, cuuint32_t rows, const char* what) {
     cuuint64_t dims[4] = {ch, W, W, F};
     cuuint64_t str[3] = {ch * 2, ch * 2 * W, ch * 2 * W * W};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(kChWP), rows, 1};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(W + 2), rows, 1};
     return encode_tiled(h, m, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
   };
   auto w2d = [&](CUtensorMap* m, const void* base, cuuint64_t K, cuuint64_t rows, cuuint32_t box_rows, const char* what) {
@@ -477,33 +481,36 @@ int build_chain_maps(phdfx_t* h, const phdfx_layer_desc& c2, const phdfx_layer_d
     cuuint32_t box[2] = {64, box_rows};
     return encode_tiled(h, m, base, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
   };
-  if (int rc = act4(&cp->mH, t1, 64, kChRT + 2, "chain t1 patch")) return rc;
+  if (int rc = act4(&cp->mH, t1, C2, rt + 2, "chain t1 patch")) return rc;
   if (cp->has_ds)
-    if (int rc = act4(&cp->mX, x, 64, kChRT, "chain down-sample source")) return rc;
-  if (int rc = act4(&cp->mO, out, 256, kChRT, "chain out")) return rc;
+    if (int rc = act4(&cp->mX, x, 64, rt, "chain down-sample source")) return rc;
+  if (int rc = act4(&cp->mO, out, N3, rt, "chain out")) return rc;
   if (!cp->has_ds)
-    if (int rc = act4(&cp->mR, res, 256, kChRT, "chain residual")) return rc;
+    if (int rc = act4(&cp->mR, res, N3, rt, "chain residual")) return rc;
   if (c1)
-    if (int rc = act4(&cp->mT, t1n, c1->cout, kChRT, "chain next t1")) return rc;
-  if (int rc = w2d(&cp->mW2, h->d_weights + c2.w_off, 576, 64, 64, "chain W2")) return rc;
-  if (int rc = w2d(&cp->mW3, h->d_weights + c3.w_off, cp->has_ds ? 128 : 64, 256, 256, "chain W3")) return rc;
+    if (int rc = act4(&cp->mT, t1n, c1->cout, rt, "chain next t1")) return rc;
+  if (int rc = w2d(&cp->mW2, h->d_weights + c2.w_off, 9 * C2, C2, static_cast<cuuint32_t>(C2), "chain W2")) return rc;
+  // conv3 weights: resident as [256 rows][64 K] blocks when N3 = 256, streamed as [128 rows][64 K] tiles when 512
+  if (int rc = w2d(&cp->mW3, h->d_weights + c3.w_off, C2 + (cp->has_ds ? 64 : 0), N3, N3 == 256 ? 256 : 128, "chain W3"))
+    return rc;
   if (c1)
     if (int rc = w2d(&cp->mW1, h->d_weights + c1->w_off, 256, c1->cout, 64, "chain W1n")) return rc;
   return 0;
 }
 
-template <bool HAS_DS, int N1>
-int launch_chain_t(phdfx_t* h, const ChainPlan& cp, const ChainParams& p, cudaStream_t st) {
-  using Cfg = ChainCfg<HAS_DS, N1>;
+template <int W, int C2, int N3, bool HAS_DS, int N1>
+int launch_chain_t(phdfx_t* h, const ChainPlan& cp, ChainParams p, cudaStream_t st) {
+  using Cfg = ChainCfg<W, C2, N3, HAS_DS, N1>;
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {
-    CUDA_TRY(h, cudaFuncSetAttribute(bottleneck_chain_kernel<HAS_DS, N1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::SMEM_BYTES));
+    CUDA_TRY(h, cudaFuncSetAttribute(bottleneck_chain_kernel<W, C2, N3, HAS_DS, N1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[h->device & 63] = true;
   }
+  p.num_tiles = p.n_frames * Cfg::TILES_PER_FRAME;
   const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
-  CUDA_TRY(h, launch_pdl(bottleneck_chain_kernel<HAS_DS, N1>, dim3(grid), dim3(kChainThreads), Cfg::SMEM_BYTES, st,
-                         cp.mH, cp.mX, cp.mW2, cp.mW3, cp.mW1, cp.mO, cp.mR, cp.mT, p));
+  CUDA_TRY(h, launch_pdl(bottleneck_chain_kernel<W, C2, N3, HAS_DS, N1>, dim3(grid), dim3(kChainThreads),
+                         Cfg::SMEM_BYTES, st, cp.mH, cp.mX, cp.mW2, cp.mW3, cp.mW1, cp.mO, cp.mR, cp.mT, p));
   h->last_launches++;
   return 0;
 }
@@ -513,16 +520,18 @@ int launch_chain(phdfx_t* h, const ChainPlan& cp, int n, cudaStream_t st, int re
   const auto& c3 = h->layers[cp.first + 1];
   ChainParams p{};
   p.n_frames = n;
-  p.num_tiles = n * kChTilesPerFrame;
   p.rev = rev;
   p.bias2 = h->d_bias + c2.b_off;
   p.bias3 = h->d_bias + c3.b_off;
   p.bias1n = cp.n1 ? h->d_bias + h->layers[cp.first + 2].b_off : nullptr;
   p.trace = trace;
-  if (cp.has_ds) return cp.n1 == 64 ? launch_chain_t<true, 64>(h, cp, p, st) : launch_chain_t<true, 0>(h, cp, p, st);
-  if (cp.n1 == 64) return launch_chain_t<false, 64>(h, cp, p, st);
-  if (cp.n1 == 128) return launch_chain_t<false, 128>(h, cp, p, st);
-  return launch_chain_t<false, 0>(h, cp, p, st);
+  if (cp.w == 28) return launch_chain_t<28, 128, 512, false, 0>(h, cp, p, st);
+  if (cp.has_ds)
+    return cp.n1 == 64 ? launch_chain_t<56, 64, 256, true, 64>(h, cp, p, st)
+                       : launch_chain_t<56, 64, 256, true, 0>(h, cp, p, st);
+  if (cp.n1 == 64) return launch_chain_t<56, 64, 256, false, 64>(h, cp, p, st);
+  if (cp.n1 == 128) return launch_chain_t<56, 64, 256, false, 128>(h, cp, p, st);
+  return launch_chain_t<56, 64, 256, false, 0>(h, cp, p, st);
 }
 
 // Fused stem + max-pool (stem_pool_sm100.cuh).  `out` receives [n][56][56][64] bf16.
@@ -777,8 +786,17 @@ int phdfx_nchw_f32_to_nhwc_bf16(phdfx_t* h, const float* d_x, int n, void* d_out
   return 0;
 }
 
-static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cudaStream_t st) {
+static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cudaStream_t st,
+                        std::vector<cudaEvent_t>* marks = nullptr) {
   if (!d_feats) return fail(h, PHDFX_ERR_INVALID, "phdfx_forward: null d_feats");
+  // profiling hook (phdfx_forward_timed): an event before every launch and one after the last
+  auto mark = [&]() {
+    if (!marks) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    marks->push_back(e);
+  };
   bool wrote_feats = false;
   int launch_no = 0;
   for (size_t i = 0; i < h->layers.size(); ++i, ++launch_no) {
@@ -788,6 +806,7 @@ static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cud
     const void* res = L.res_buf >= 0 ? h->bufs[L.res_buf] : nullptr;
     // serpentine: odd launches walk their tiles backwards, i.e. start where the previous launch ended
     const int rev = (g_use_rev && (launch_no & 1)) ? 1 : 0;
+    mark();
     if (h->chain_at[i] >= 0) {
       const ChainPlan& cp = h->chains[h->chain_at[i]];
       if (int rc = launch_chain(h, cp, n, st, rev)) return rc;
@@ -815,6 +834,7 @@ static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cud
     }
     if (L.gap) wrote_feats = true;
   }
+  mark();
   if (!wrote_feats) return fail(h, PHDFX_ERR_STATE, "layer list has no gap layer: nothing wrote d_feats");
   return 0;
 }
@@ -824,6 +844,28 @@ int phdfx_forward(phdfx_t* h, const void* d_in, int n, float* d_feats, void* str
   CUDA_TRY(h, cudaSetDevice(h->device));
   h->last_launches = 0;
   return forward_impl(h, d_in, n, d_feats, static_cast<cudaStream_t>(stream));
+}
+
+int phdfx_forward_timed(phdfx_t* h, const void* d_in, int n, float* d_feats, void* stream, float* ms_per_launch,
+                        int cap) {
+  if (int rc = check_ready(h, n)) return rc;
+  if (!ms_per_launch || cap < 1) return fail(h, PHDFX_ERR_INVALID, "phdfx_forward_timed: null/empty output array");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  h->last_launches = 0;
+  std::vector<cudaEvent_t> marks;
+  int rc = forward_impl(h, d_in, n, d_feats, static_cast<cudaStream_t>(stream), &marks);
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  int count = 0;
+  for (size_t i = 0; i + 1 < marks.size(); ++i) {
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, marks[i], marks[i + 1]);
+    if (static_cast<int>(i) < cap) ms_per_launch[i] = ms;
+    ++count;
+  }
+  for (cudaEvent_t ev : marks) cudaEventDestroy(ev);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(h, PHDFX_ERR_CUDA, "phdfx_forward_timed: %s", cudaGetErrorString(e));
+  return count;
 }
 
 int phdfx_extract_u8(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const int32_t* d_boxes, int flip_w,

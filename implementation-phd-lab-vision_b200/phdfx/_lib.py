@@ -21,6 +21,7 @@ EXPORTS = [
     "phdfx_preprocess_u8",
     "phdfx_nchw_f32_to_nhwc_bf16",
     "phdfx_forward",
+    "phdfx_forward_timed",
     "phdfx_extract_u8",
     "phdfx_run_layer",
     "phdfx_run_layer2",
@@ -97,6 +98,8 @@ def load() -> C.CDLL:
     lib.phdfx_nchw_f32_to_nhwc_bf16.argtypes = [vp, vp, i32, vp, vp]
     lib.phdfx_forward.restype = i32
     lib.phdfx_forward.argtypes = [vp, vp, i32, vp, vp]
+    lib.phdfx_forward_timed.restype = i32
+    lib.phdfx_forward_timed.argtypes = [vp, vp, i32, vp, vp, C.POINTER(C.c_float), i32]
     lib.phdfx_extract_u8.restype = i32
     lib.phdfx_extract_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp]
     lib.phdfx_run_layer.restype = i32

@@ -173,6 +173,27 @@ class B200Backbone:
             _lib.check(self._lib.phdfx_forward(self._h, x.data_ptr(), n, feats.data_ptr(), self._stream()), self._h)
         return feats
 
+    @torch.no_grad()
+    def forward_timed(self, x: torch.Tensor):
+        """Trunk on an NHWC4p bf16 input with every launch timed in situ (CUDA events between launches).
+        Returns (features, [(name, ms), ...]); a fused chain is one entry named after the layers it covers."""
+        self._check_dev(x, "x")
+        n = x.shape[0]
+        feats = torch.empty(n, self.FEAT_DIM, device=self.device, dtype=torch.float32)
+        cap = len(self.plan.layers)
+        ms = (C.c_float * cap)()
+        with torch.cuda.device(self.device):
+            cnt = self._lib.phdfx_forward_timed(self._h, x.data_ptr(), n, feats.data_ptr(), self._stream(), ms, cap)
+        if cnt < 0:
+            _lib.check(cnt, self._h)
+        names, i = [], 0
+        while i < len(self.plan.layers):
+            span = max(1, self.chain_span(i))
+            names.append("+".join(self.plan.names[i:i + span]))
+            i += span
+        assert len(names) == cnt, (len(names), cnt)
+        return feats, list(zip(names, [float(v) for v in ms[:cnt]]))
+
     # ---- per-layer hook --------------------------------------------------------------------------------------------
     @torch.no_grad()
     def run_layer(self, layer_id: int, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
@@ -214,19 +235,27 @@ class B200Backbone:
 
     @torch.no_grad()
     def run_chain(self, first_layer_id: int, t1: torch.Tensor, x_or_res: torch.Tensor):
-        """Run the fused layer1 chain that starts at conv2 = `first_layer_id` on explicit NHWC bf16 tensors:
-        t1 [n,56,56,64], x_or_res = down-sample source [n,56,56,64] or identity residual [n,56,56,256].
-        Returns (out [n,56,56,256], next block's t1 [n,56,56,cout] or None)."""
+        """Run the fused bottleneck chain that starts at conv2 = `first_layer_id` on explicit NHWC bf16 tensors:
+        t1 [n,H,H,width], x_or_res = down-sample source [n,H,H,64] or identity residual [n,H,H,4*width]
+        (H, width = 56, 64 in layer1; 28, 128 in layer2).
+        Returns (out [n,H,H,4*width], next block's t1 [n,H,H,cout] or None)."""
         span = self.chain_span(first_layer_id)
         if span == 0:
             raise RuntimeError(f"no fused chain starts at layer {first_layer_id}")
         self._check_dev(t1, "t1")
         self._check_dev(x_or_res, "x_or_res")
         n = t1.shape[0]
-        out = torch.empty(n, 56, 56, 256, device=self.device, dtype=torch.bfloat16)
+        L3 = self.plan.layers[first_layer_id + 1]
+        hw = L3.hin
+        if tuple(t1.shape[1:]) != (hw, hw, L3.cin):
+            raise RuntimeError(f"t1 must be [n,{hw},{hw},{L3.cin}], got {tuple(t1.shape)}")
+        want_c = L3.cin2 if L3.in2_buf >= 0 else L3.cout
+        if tuple(x_or_res.shape) != (n, hw, hw, want_c):
+            raise RuntimeError(f"x_or_res must be [{n},{hw},{hw},{want_c}], got {tuple(x_or_res.shape)}")
+        out = torch.empty(n, hw, hw, L3.cout, device=self.device, dtype=torch.bfloat16)
         t1n = None
         if span == 3:
-            t1n = torch.empty(n, 56, 56, self.plan.layers[first_layer_id + 2].cout, device=self.device,
+            t1n = torch.empty(n, hw, hw, self.plan.layers[first_layer_id + 2].cout, device=self.device,
                               dtype=torch.bfloat16)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.phdfx_run_chain(self._h, first_layer_id, t1.data_ptr(), x_or_res.data_ptr(),

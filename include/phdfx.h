@@ -97,6 +97,13 @@ int phdfx_nchw_f32_to_nhwc_bf16(phdfx_t* h, const float* d_x_nchw, int n, void* 
  * d_feats: fp32 [n][2048]. */
 int phdfx_forward(phdfx_t* h, const void* d_in_nhwc4p, int n, float* d_feats, void* stream);
 
+/* Profiling hook (BASELINE config 3): phdfx_forward with a CUDA event before every launch and after the last one.
+ * Synchronises the stream (NOT graph-capturable), writes the elapsed milliseconds of each launch — in situ, i.e. with
+ * the L2 contents the previous launch left — into the HOST array ms_per_launch[cap] and returns the number of
+ * launches (> 0), or a negative status.  The events serialise the launches (no programmatic overlap). */
+int phdfx_forward_timed(phdfx_t* h, const void* d_in_nhwc4p, int n, float* d_feats, void* stream,
+                        float* ms_per_launch, int cap);
+
 /* Seam B: preprocess + trunk. */
 int phdfx_extract_u8(phdfx_t* h, const uint8_t* d_frames_hwc, int n, int H, int W, const int32_t* d_boxes,
                      int flip_w, float* d_feats, void* stream);
@@ -109,14 +116,15 @@ int phdfx_run_layer(phdfx_t* h, int layer_id, const void* d_in, const void* d_re
 int phdfx_run_layer2(phdfx_t* h, int layer_id, const void* d_in, const void* d_in2, const void* d_residual,
                      void* d_out, int n, void* stream);
 
-/* Fused spans.  phdfx_forward runs layer1's  conv2 (3x3) -> conv3 (+ identity | fused down-sample) [-> the next
- * block's conv1]  (resnet.py:150-161 and the following :146-148) as ONE launch (bottleneck_chain_sm100.cuh) whenever the
- * execution list has that pattern with distinct buffers; PHDFX_NO_CHAIN=1 in the environment at phdfx_create keeps
- * the per-conv kernels.  phdfx_chain_span: number of list entries the launch starting at layer_id covers (0 = no fused
- * launch starts there).  phdfx_run_chain: that launch on caller buffers (parity tests / per-kernel benchmark):
- * d_t1 = conv2's input [n][56][56][64]; d_x_or_res = the down-sample source [n][56][56][64] when conv3 carries a
- * second input, else the identity residual [n][56][56][256]; d_out = block output [n][56][56][256]; d_t1_next = the
- * trailing conv1's output [n][56][56][cout] (NULL when the span is 2).  All NHWC bf16. */
+/* Fused spans.  phdfx_forward runs  conv2 (3x3) -> conv3 (+ identity | fused down-sample) [-> the next block's conv1]
+ * (resnet.py:150-161 and the following :146-148) as ONE launch (bottleneck_chain_sm100.cuh) for the stride-1 blocks of
+ * layer1 (56x56, width 64; the next conv1 rides along) and layer2 (28x28, width 128) whenever the execution list has
+ * that pattern with distinct buffers; PHDFX_NO_CHAIN=1 in the environment at phdfx_create keeps the per-conv kernels.
+ * phdfx_chain_span: number of list entries the launch starting at layer_id covers (0 = no fused launch starts there).
+ * phdfx_run_chain: that launch on caller buffers (parity tests / per-kernel benchmark): d_t1 = conv2's input
+ * [n][H][H][width]; d_x_or_res = the down-sample source [n][H][H][64] when conv3 carries a second input, else the
+ * identity residual [n][H][H][4*width]; d_out = block output [n][H][H][4*width]; d_t1_next = the trailing conv1's
+ * output [n][H][H][cout] (NULL when the span is 2).  All NHWC bf16. */
 int phdfx_chain_span(const phdfx_t* h, int layer_id);
 int phdfx_run_chain(phdfx_t* h, int first_layer_id, const void* d_t1, const void* d_x_or_res, void* d_out,
                     void* d_t1_next, int n, void* stream);

@@ -209,20 +209,21 @@ def _chain_reference(eng, mods, first, t1, x_or_res):
     return out.permute(0, 2, 3, 1), t1n
 
 
-@pytest.mark.parametrize("n", [1, 3, 11])
-def test_layer1_chain_kernel_vs_fp32_torch(eng, backbone, n):
+@pytest.mark.parametrize("n", [1, 3, 11, 29])
+def test_chain_kernel_vs_fp32_torch(eng, backbone, n):
     """bottleneck_chain_kernel (conv2 -> conv3 [+identity | +down-sample] [-> next conv1] in one launch), every
-    variant the plan uses, on explicit tensors.  n = 11 gives each CTA of a 148-SM grid several tiles (the software
-    pipeline across tiles), n = 1 fewer tiles than SMs."""
+    variant the plan uses (three in layer1, the streamed-conv3 one in layer2), on explicit tensors.  n = 11 / 29 give
+    each CTA of a 148-SM grid several tiles (the software pipeline across tiles), n = 1 fewer tiles than SMs."""
     mods = _layer_modules(backbone)
     g = torch.Generator(device="cuda").manual_seed(300 + n)
     firsts = [i for i in range(len(eng.plan.layers)) if eng.chain_span(i) > 0]
-    assert [eng.chain_span(i) for i in firsts] == [3, 3, 3]
+    assert [eng.chain_span(i) for i in firsts] == [3, 3, 3, 2, 2, 2]
     for first in firsts:
         L3 = eng.plan.layers[first + 1]
-        t1 = torch.relu(torch.randn(n, 56, 56, 64, device="cuda", generator=g)).to(torch.bfloat16)
-        c = 64 if L3.in2_buf >= 0 else 256
-        xr = torch.randn(n, 56, 56, c, device="cuda", generator=g).to(torch.bfloat16)
+        hw = L3.hin
+        t1 = torch.relu(torch.randn(n, hw, hw, L3.cin, device="cuda", generator=g)).to(torch.bfloat16)
+        c = L3.cin2 if L3.in2_buf >= 0 else L3.cout
+        xr = torch.randn(n, hw, hw, c, device="cuda", generator=g).to(torch.bfloat16)
         out, t1n = eng.run_chain(first, t1, xr)
         ref_out, ref_t1n = _chain_reference(eng, mods, first, t1, xr)
         err = (out.float() - ref_out).abs().max().item() / ref_out.abs().max().item()
@@ -232,19 +233,19 @@ def test_layer1_chain_kernel_vs_fp32_torch(eng, backbone, n):
             assert err < 1e-2, f"{eng.plan.names[first + 2]}: next t1 normalised error {err}"
 
 
-def test_layer1_chain_is_bit_identical_to_per_conv_kernels(backbone):
+def test_chains_are_bit_identical_to_per_conv_kernels(backbone):
     """The fused chain performs the same MMAs in the same order with the same roundings as the three kernels it
     replaces: features are bit-identical with PHDFX_NO_CHAIN=1, at a batch that gives every CTA several tiles."""
-    frames = torch.from_numpy(R.seeded_frames(24, 224, 224, 41)).cuda()
-    fused = phdfx.B200Backbone(backbone, device=0, max_frames=24)
+    frames = torch.from_numpy(R.seeded_frames(64, 224, 224, 41)).cuda()
+    fused = phdfx.B200Backbone(backbone, device=0, max_frames=64)
     os.environ["PHDFX_NO_CHAIN"] = "1"
     try:
-        plain = phdfx.B200Backbone(backbone, device=0, max_frames=24)
+        plain = phdfx.B200Backbone(backbone, device=0, max_frames=64)
     finally:
         del os.environ["PHDFX_NO_CHAIN"]
     a = fused.extract_u8(frames, None)
     b = plain.extract_u8(frames, None)
-    assert fused.launches == 44 and plain.launches == 50
+    assert fused.launches == 41 and plain.launches == 50
     assert torch.equal(a, b)
     fused.close()
     plain.close()
@@ -259,12 +260,12 @@ def test_unfused_stem_and_maxpool_kernels(backbone, n):
     frames = torch.from_numpy(R.seeded_frames(n, 224, 224, 31)).cuda()
     a = fused.extract_u8(frames, None)
     b = unfused.extract_u8(frames, None)
-    assert fused.launches == 44 and unfused.launches == 45
+    assert fused.launches == 41 and unfused.launches == 42
     assert torch.equal(a, b)
     # separate down-sample launches + residual add (rounds the branch to bf16 first): same features within bf16 noise
     plain = phdfx.B200Backbone(backbone, device=0, max_frames=4, fuse_downsample=False)
     c = plain.extract_u8(frames, None)
-    assert plain.launches == 50
+    assert plain.launches == 47
     err, cos = frame_errors(c.cpu().numpy(), a.cpu().numpy())
     assert err.max() < 1e-2 and cos.min() > 0.9999
     plain.close()
@@ -391,7 +392,7 @@ def test_cuda_graph_replay_is_bit_identical(eng):
     assert torch.equal(g.replay(), eng.extract_u8(frames[:10].contiguous(), boxes[:10].contiguous()))
     buf.copy_(frames[10:])
     assert torch.equal(g.replay(), eng.extract_u8(frames[10:].contiguous(), boxes[10:].contiguous()))
-    assert g.launches == 44
+    assert g.launches == 41
 
 
 def test_errors_are_loud(eng):
@@ -416,9 +417,9 @@ def test_full_batch_256_properties():
     e = phdfx.B200Backbone(bb, device=0, max_frames=256)
     frames = torch.from_numpy(R.seeded_frames(256, 224, 224, 13)).cuda()
     big = e.extract_u8(frames, None)
-    # K1 + fused stem/maxpool + 42 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 -> next conv1
-    # chains are one launch each), all ours
-    assert e.launches == 44
+    # K1 + fused stem/maxpool + 39 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 -> next conv1
+    # chains and layer2's conv2 -> conv3 chains are one launch each), all ours
+    assert e.launches == 41
     small = torch.cat([e.extract_u8(frames[i:i + 37].contiguous(), None) for i in range(0, 256, 37)])
     assert torch.equal(big, small)
     assert torch.isfinite(big).all()

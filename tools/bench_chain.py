@@ -45,8 +45,9 @@ def main():
             continue
         L3 = eng.plan.layers[first + 1]
         ds = L3.in2_buf >= 0
-        t1 = torch.relu(torch.randn(n, 56, 56, 64, device="cuda", generator=g)).to(torch.bfloat16)
-        xr = torch.randn(n, 56, 56, 64 if ds else 256, device="cuda", generator=g).to(torch.bfloat16)
+        hw, c2, n3 = L3.hin, L3.cin, L3.cout
+        t1 = torch.relu(torch.randn(n, hw, hw, c2, device="cuda", generator=g)).to(torch.bfloat16)
+        xr = torch.randn(n, hw, hw, 64 if ds else n3, device="cuda", generator=g).to(torch.bfloat16)
         ms = timed(lambda: eng.run_chain(first, t1, xr), flush, reps)
         # the per-conv kernels on the same data
         t2 = eng.run_layer(first, t1)
@@ -61,9 +62,9 @@ def main():
         if span == 3:
             parts.append(timed(lambda: eng.run_layer(first + 2, out), flush, reps))
             n1 = eng.plan.layers[first + 2].cout
-        px = n * 56 * 56
-        macs = px * (64 * 576 + 256 * (128 if ds else 64) + 256 * n1)
-        alg = px * 2 * (64 + (64 if ds else 256) + 256 + n1)
+        px = n * hw * hw
+        macs = px * (c2 * 9 * c2 + n3 * (c2 + (64 if ds else 0)) + n3 * n1)
+        alg = px * 2 * (c2 + (64 if ds else n3) + n3 + n1)
         rows.append({"first": first, "name": "+".join(eng.plan.names[first:first + span]), "ms": round(ms, 4),
                      "per_conv_ms": [round(p, 4) for p in parts], "per_conv_sum_ms": round(sum(parts), 4),
                      "tflops": round(2 * macs / (ms / 1e3) / 1e12, 1), "alg_gbs": round(alg / (ms / 1e3) / 1e9, 1)})

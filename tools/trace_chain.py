@@ -21,7 +21,7 @@ import resnet50_ref as R  # noqa: E402
 
 EV = {0: "mma conv2 start", 1: "mma conv2 issued", 2: "mma conv3 issue", 3: "mma conv1n start", 4: "mma conv1n issued",
       5: "epi A start", 6: "epi A end", 7: "epi B start", 8: "epi B g0", 9: "epi B g1", 10: "epi B g2", 11: "epi B g3",
-      12: "epi C start", 13: "epi C end", 14: "epi res loads issued", 15: "halo load issue", 16: "dma S0", 17: "dma S1",
+      12: "epi C start", 13: "epi C end", 14: "epi B.hi start", 15: "halo load issue", 16: "dma S0", 17: "dma S1",
       18: "dma S2", 19: "dma S3", 20: "dma S4", 21: "dma S5", 22: "res load B0 issue"}
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
@@ -30,9 +30,10 @@ g = torch.Generator(device="cuda").manual_seed(0)
 for first in range(len(eng.plan.layers)):
     if eng.chain_span(first) == 0:
         continue
-    ds = eng.plan.layers[first + 1].in2_buf >= 0
-    t1 = torch.relu(torch.randn(n, 56, 56, 64, device="cuda", generator=g)).to(torch.bfloat16)
-    xr = torch.randn(n, 56, 56, 64 if ds else 256, device="cuda", generator=g).to(torch.bfloat16)
+    L3 = eng.plan.layers[first + 1]
+    ds = L3.in2_buf >= 0
+    t1 = torch.relu(torch.randn(n, L3.hin, L3.hin, L3.cin, device="cuda", generator=g)).to(torch.bfloat16)
+    xr = torch.randn(n, L3.hin, L3.hin, 64 if ds else L3.cout, device="cuda", generator=g).to(torch.bfloat16)
     eng.run_chain(first, t1, xr)
     torch.cuda.synchronize()
 blocks = open(raw).read().strip().split("chain ")[1:]
