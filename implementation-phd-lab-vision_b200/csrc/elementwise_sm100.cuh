@@ -100,10 +100,19 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
     const uint8_t* t0 = s0 + off0;
     const uint8_t* t1 = need1 ? s1 + off1 : t0;
     const float scale_w = __fdiv_rn(static_cast<float>(bw), static_cast<float>(kImg));
+    // a 224x224 crop: F.resize returns its input untouched (torchvision transforms/functional.py:470-471); the stencil
+    // below degenerates to weight 1 on v00 and +0 elsewhere, i.e. the same bytes — skip the arithmetic
+    const bool ident = (bh == kImg) && (bw == kImg);
     for (int wp = lane; wp < kStemWPad; wp += 32) {
       uint2 o = make_uint2(0u, 0u);
       int x = wp - kStemLeftPad;
-      if (x >= 0 && x < kImg) {
+      if (x >= 0 && x < kImg && ident) {
+        if (flip_w) x = kImg - 1 - x;
+        const uint16_t* l16 = reinterpret_cast<const uint16_t*>(lut);
+        const uint32_t r0v = l16[t0[x * 3 + 0]], r1v = l16[256 + t0[x * 3 + 1]], r2v = l16[512 + t0[x * 3 + 2]];
+        o.x = r0v | (r1v << 16);
+        o.y = r2v;
+      } else if (x >= 0 && x < kImg) {
         if (flip_w) x = kImg - 1 - x;
         float sx = __fmaf_rn(scale_w, static_cast<float>(x) + 0.5f, -0.5f);
         sx = sx < 0.0f ? 0.0f : sx;
