@@ -636,6 +636,10 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   h->max_frames = max_frames;
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("PHDFX_NO_CHAIN")) h->use_chain = !(e[0] == '1');
+  if (const char* e = getenv("PHDFX_SM_CAP")) {  // experiments: run every persistent grid on fewer SMs
+    const int cap = atoi(e);
+    if (cap >= 2 && cap < h->num_sms) h->num_sms = cap & ~1;
+  }
   if (int rc = resolve_driver(h)) {
     delete h;
     return rc;

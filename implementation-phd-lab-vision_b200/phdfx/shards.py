@@ -16,6 +16,12 @@ remainder carried over; the final flush shuffles once more and writes full shard
 
 What differs is the mechanics: rows are written once into a preallocated shard tensor instead of
 `torch.stack` over up to 2048 small tensors, and files are written by a bounded background thread.
+
+Multi-GPU runs do not funnel features through one writer at all: which clip lands in which row of
+which shard is a pure function of (n_clips, shard_size, shuffle_pool, shuffle_seed) — `plan_shards` replays the
+reference's pooling / shuffling on clip NUMBERS — so every rank extracts exactly the clips of the shards it owns and
+writes those files itself (`assemble_shard`), and rank 0 writes `index.pt` from the plan (`index_from_plan`).  The
+output holds exactly what the single-process writer produces (same index, same tensors, same row order).
 """
 from __future__ import annotations
 
@@ -82,6 +88,82 @@ class ClipRecord:
         self.feats, self.joints3d, self.joints2d, self.K, self.metas = feats, joints3d, joints2d, K, metas
 
 
+def assemble_shard(groups: Sequence[ClipRecord], n_vars: int) -> dict:
+    """The shard dict of `groups` (one ClipRecord per clip, variants contiguous): rows filled in place."""
+    rows = len(groups) * n_vars
+    g0 = groups[0]
+    feats = torch.empty((rows,) + tuple(g0.feats[0].shape), dtype=g0.feats[0].dtype)
+    j3 = torch.empty((rows,) + tuple(g0.joints3d[0].shape), dtype=g0.joints3d[0].dtype)
+    j2 = torch.empty((rows,) + tuple(g0.joints2d[0].shape), dtype=g0.joints2d[0].dtype)
+    Ks = torch.empty((rows,) + tuple(g0.K[0].shape), dtype=g0.K[0].dtype)
+    metas = []
+    for i, g in enumerate(groups):
+        base = i * n_vars
+        for v in range(n_vars):
+            feats[base + v] = g.feats[v]
+            j3[base + v] = g.joints3d[v]
+            j2[base + v] = g.joints2d[v]
+            Ks[base + v] = g.K[v]
+            metas.append(g.metas[v])
+    return {"feats": feats, "joints3d": j3, "joints2d": j2, "K": Ks, "meta": metas, "n_vars": n_vars}
+
+
+def shard_path(out_root, shard_id: int) -> Path:
+    return Path(out_root) / f"shard_{shard_id:05d}.pt"
+
+
+def plan_shards(n_clips: int, shard_size: int, shuffle_pool: int, shuffle_seed: int) -> List[List[int]]:
+    """Clip numbers (dataset order) of every shard, in row order: the reference's pooling and shuffling
+    (src/preprocess_resnet_features.py:94-131, 269, 325-396) replayed on integers.  `random.Random.shuffle` draws
+    depend only on the list length, so this is exactly the permutation the streaming writer applies to clip records."""
+    rng = random.Random(shuffle_seed)
+    pool: List[int] = []
+    carry: List[int] = []
+    shards: List[List[int]] = []
+
+    def flush(final: bool):
+        nonlocal pool, carry
+        combined = carry + pool
+        rng.shuffle(combined)
+        n_full = len(combined) // shard_size
+        for s in range(n_full):
+            shards.append(combined[s * shard_size:(s + 1) * shard_size])
+        rest = combined[n_full * shard_size:]
+        pool = []
+        if final:
+            if rest:
+                shards.append(rest)
+            carry = []
+        else:
+            carry = rest
+
+    for i in range(n_clips):
+        pool.append(i)
+        if len(pool) >= shuffle_pool:
+            flush(False)
+    flush(True)
+    return shards
+
+
+def index_from_plan(plan: Sequence[Sequence[int]], clip_meta, n_vars: int, seq_len: int, frame_skip: int,
+                    save_fp16: bool, augment: bool, shuffle_seed: int, shuffle_pool: int) -> dict:
+    """`index.pt` content for a planned run.  clip_meta(i) -> object/dict with subject, action, cam, start, end of
+    clip i (the dataset's own index entry)."""
+    clips = []
+    for sid, ids in enumerate(plan):
+        for row, i in enumerate(ids):
+            m = clip_meta(i)
+            get = (lambda k: m[k]) if isinstance(m, dict) else (lambda k: getattr(m, k))
+            clips.append({"shard_id": sid, "row": row * n_vars, "subject": get("subject"), "action": get("action"),
+                          "cam": get("cam"), "start": get("start"), "end": get("end")})
+    return {
+        "clips": clips, "n_shards": len(plan), "n_clips": sum(len(ids) for ids in plan), "n_variants": n_vars,
+        "aug_names": list(AUG_NAMES) if augment else ["orig"], "seq_len": seq_len, "frame_skip": frame_skip,
+        "feat_dtype": "float16" if save_fp16 else "float32", "variants_grouped": True, "shuffle_seed": shuffle_seed,
+        "shuffle_pool": shuffle_pool,
+    }
+
+
 class ShardWriter:
     def __init__(self, out_root, n_vars: int, shard_size: int = 512, shuffle_pool: int = 8192,
                  shuffle_seed: int = 123, writer: Optional[AsyncShardWriter] = None):
@@ -102,27 +184,12 @@ class ShardWriter:
 
     # ---- write one shard: rows filled in place -----------------------------------------------------------------
     def _write_shard(self, groups: List[ClipRecord]):
-        rows = len(groups) * self.n_vars
-        g0 = groups[0]
-        feats = torch.empty((rows,) + tuple(g0.feats[0].shape), dtype=g0.feats[0].dtype)
-        j3 = torch.empty((rows,) + tuple(g0.joints3d[0].shape), dtype=g0.joints3d[0].dtype)
-        j2 = torch.empty((rows,) + tuple(g0.joints2d[0].shape), dtype=g0.joints2d[0].dtype)
-        Ks = torch.empty((rows,) + tuple(g0.K[0].shape), dtype=g0.K[0].dtype)
-        metas = []
         for i, g in enumerate(groups):
-            base = i * self.n_vars
             m0 = g.metas[0]
-            self.clip_index.append({"shard_id": self.shard_id, "row": base, "subject": m0["subject"],
+            self.clip_index.append({"shard_id": self.shard_id, "row": i * self.n_vars, "subject": m0["subject"],
                                     "action": m0["action"], "cam": m0["cam"], "start": m0["start"],
                                     "end": m0["end"]})
-            for v in range(self.n_vars):
-                feats[base + v] = g.feats[v]
-                j3[base + v] = g.joints3d[v]
-                j2[base + v] = g.joints2d[v]
-                Ks[base + v] = g.K[v]
-                metas.append(g.metas[v])
-        shard = {"feats": feats, "joints3d": j3, "joints2d": j2, "K": Ks, "meta": metas, "n_vars": self.n_vars}
-        self.writer.save(shard, self.out_root / f"shard_{self.shard_id:05d}.pt")
+        self.writer.save(assemble_shard(groups, self.n_vars), shard_path(self.out_root, self.shard_id))
         self.shard_id += 1
 
     def _flush(self, final: bool):

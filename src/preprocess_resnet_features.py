@@ -11,6 +11,10 @@ torch.compile, one process per GPU instead of nn.DataParallel (:214-217), pinned
     torchrun --nproc-per-node 8 src/preprocess_resnet_features.py --root ROOT --out OUT ...     # 8 GPUs
     python -u src/preprocess_resnet_features.py --synthetic 64:224x224 --out OUT --weights random:0   # no dataset
 
+With more than one process the default is the shard-parallel writer (--multi-gpu-writer sharded): the shard plan is
+computed up front from (n_clips, shard-size, shuffle-pool, shuffle-seed), rank r extracts the clips of shards
+r, r + world, ... and writes those files itself; rank 0 adds index.pt.  The files hold exactly what a one-process run writes.
+
 Real data needs the user's `dataset.py` (the reference's `Human36MPreprocessedClips`, which owns video decoding and
 annotation handling — outside this drop-in) importable, e.g. by running from the reference's src/ directory or with
 --dataset-path.  Extra flags: --backend {b200,torch}, --synthetic, --weights, --dataset-path, --max-clips.
@@ -30,7 +34,8 @@ _ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(_ROOT / "implementation-phd-lab-vision_b200"))
 
 from phdfx.dist import gather_rows, shard_range  # noqa: E402
-from phdfx.shards import AUG_NAMES, ClipRecord, ShardWriter  # noqa: E402
+from phdfx.shards import (AUG_NAMES, AsyncShardWriter, ClipRecord, ShardWriter, assemble_shard,  # noqa: E402
+                          index_from_plan, plan_shards, shard_path)
 from phdfx.synthetic import SyntheticH36MClips  # noqa: E402
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
@@ -64,6 +69,10 @@ def parse_args(argv=None):
     p.add_argument("--dataset-path", type=str, default=None, help="directory holding the user's dataset.py")
     p.add_argument("--max-clips", type=int, default=None)
     p.add_argument("--jitter-seed", type=int, default=0, help="seed of the colour-jitter variant (synthetic mode)")
+    p.add_argument("--multi-gpu-writer", choices=["sharded", "gather"], default="sharded",
+                   help="world size > 1: 'sharded' = every rank extracts and writes the shards it owns (the shard "
+                        "composition is a pure function of the shuffle parameters; no feature gather), "
+                        "'gather' = contiguous clip ranges per rank, features gathered to rank 0, one writer")
     return p.parse_args(argv)
 
 
@@ -221,53 +230,102 @@ def main(argv=None):
             outs.append((vid - mean) / std)
         return run_normalised(torch.stack(outs))
 
+    def extract_clips(ids):
+        """Features + annotations of the clips `ids` (dataset numbers):
+        (feats [len(ids), n_vars, T, 2048] on the device in feat_dtype, [(joints3d[v], joints2d[v], K[v], box)])."""
+        feats = torch.empty(0, n_vars, T, 2048, device=device)
+        small = []  # per clip: (joints3d[v], joints2d[v], K[v], box)
+        if not ids:
+            return feats.to(feat_dtype), small
+        items = [ds[i] for i in ids] if synthetic or args.num_workers == 0 else _loader_fetch(ds, ids, args)
+        if synthetic:
+            frames = torch.stack([it[0] for it in items])
+            boxes = torch.stack([it[4] for it in items])
+            f_orig = run_u8(frames, boxes, False)
+            if args.augment:
+                f_jit = jitter_variant(frames, boxes, ids)
+                f_flip = run_u8(frames, boxes, True)
+                f_trev = torch.flip(f_orig, dims=[1])  # frames are independent: exact (SURVEY.md 8f N1)
+                feats = torch.stack([f_orig, f_jit, f_flip, f_trev], dim=1)
+            else:
+                feats = f_orig.unsqueeze(1)
+            for it in items:
+                j3, j2, K, box = it[1], it[2], it[3], it[4]
+                if args.augment:
+                    small.append(_augment_annotations(j3, j2, K))
+                else:
+                    small.append(([j3], [j2], [K], box))
+        else:
+            if args.augment:  # item = list of 4 (video, j3d, j2d, K) variants (src/dataset.py:411-426)
+                vids = [torch.stack([it[v][0] for it in items]) for v in range(n_vars)]
+                f = [run_normalised(vids[0]), run_normalised(vids[1]), run_normalised(vids[2])]
+                f.append(torch.flip(f[0], dims=[1]))  # trev == reversed orig (dataset.py:201-207)
+                feats = torch.stack(f, dim=1)
+                for it in items:
+                    small.append(([it[v][1] for v in range(4)], [it[v][2] for v in range(4)],
+                                  [it[v][3] for v in range(4)], None))
+            else:
+                feats = run_normalised(torch.stack([it[0] for it in items])).unsqueeze(1)
+                for it in items:
+                    small.append(([it[1]], [it[2]], [it[3]], it[4]))
+        return feats.to(feat_dtype), small
+
+    def clip_record(i, host_feats, small_i):
+        """ClipRecord of dataset clip i: host_feats [n_vars, T, 2048], small_i as returned by extract_clips."""
+        clip = ds.index[i]
+        j3s, j2s, Ks, box = small_i
+        metas = [{"subject": clip.subject, "action": clip.action, "cam": clip.cam, "start": clip.start,
+                  "end": clip.end, "aug": AUG_NAMES[v] if args.augment else "orig",
+                  "box": box if not args.augment else None} for v in range(n_vars)]
+        return ClipRecord([host_feats[v] for v in range(n_vars)], j3s, j2s, Ks, metas)
+
+    B = args.batch_size
+    t_all = time.time()
+    if world > 1 and args.multi_gpu_writer == "sharded":
+        # ---- shard-parallel: no feature gather, every rank writes the shard files it owns ------------------------
+        import torch.distributed as dist
+
+        plan = plan_shards(n_clips, args.shard_size, args.shuffle_pool, args.shuffle_seed)
+        aw = AsyncShardWriter()
+        mine = list(range(rank, len(plan), world))
+        for k, sid in enumerate(mine):
+            ids = plan[sid]
+            groups = []
+            for c0 in range(0, len(ids), B):
+                part = ids[c0:c0 + B]
+                feats, small = extract_clips(part)
+                host = feats.cpu()
+                groups.extend(clip_record(i, host[j], small[j]) for j, i in enumerate(part))
+            aw.save(assemble_shard(groups, n_vars), shard_path(out_root, sid))
+            log(f"[{100 * (k + 1) / max(1, len(mine)):5.1f}%] rank 0: shard {sid} ({len(ids)} clips) queued "
+                f"| {time.time() - t_all:6.1f}s")
+        aw.wait()
+        aw.stop()
+        dist.barrier()
+        if is_main:
+            index = index_from_plan(plan, lambda i: ds.index[i], n_vars, args.seq_len, args.frame_skip,
+                                    args.save_fp16, args.augment, args.shuffle_seed, args.shuffle_pool)
+            torch.save(index, out_root / "index.pt")
+            total = time.time() - t_all
+            log("-" * 60)
+            log(f"Done: {n_clips} clips x {n_vars} variant(s) packed into {len(plan)} shard(s) by {world} ranks")
+            log(f"Total time {total:.1f}s | {n_clips / max(total, 1e-9):.1f} clips/s "
+                f"({n_clips * n_vars * T / max(total, 1e-9):.0f} frames/s)")
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     writer = ShardWriter(out_root, n_vars, args.shard_size, args.shuffle_pool, args.shuffle_seed) if is_main else None
 
     # clips are dealt out in global batches of (world * batch_size): rank r takes the r-th contiguous slice, so
     # rank 0 can append clips to the shuffle pool in the reference's order after every gather
-    B = args.batch_size
-    t_all = time.time()
     t_last = t_all
     done = 0
     for g0 in range(0, n_clips, B * world):
         g1 = min(n_clips, g0 + B * world)
         lo, hi = shard_range(g1 - g0, rank, world)
         ids = list(range(g0 + lo, g0 + hi))
-        feats = torch.empty(0, n_vars, T, 2048, device=device)
-        small = []  # per clip: (joints3d[v], joints2d[v], K[v], box)
-        if ids:
-            items = [ds[i] for i in ids] if synthetic or args.num_workers == 0 else _loader_fetch(ds, ids, args)
-            if synthetic:
-                frames = torch.stack([it[0] for it in items])
-                boxes = torch.stack([it[4] for it in items])
-                f_orig = run_u8(frames, boxes, False)
-                if args.augment:
-                    f_jit = jitter_variant(frames, boxes, ids)
-                    f_flip = run_u8(frames, boxes, True)
-                    f_trev = torch.flip(f_orig, dims=[1])  # frames are independent: exact
-                    feats = torch.stack([f_orig, f_jit, f_flip, f_trev], dim=1)
-                else:
-                    feats = f_orig.unsqueeze(1)
-                for it in items:
-                    j3, j2, K, box = it[1], it[2], it[3], it[4]
-                    if args.augment:
-                        small.append(_augment_annotations(j3, j2, K))
-                    else:
-                        small.append(([j3], [j2], [K], box))
-            else:
-                if args.augment:  # item = list of 4 (video, j3d, j2d, K) variants (src/dataset.py:411-426)
-                    vids = [torch.stack([it[v][0] for it in items]) for v in range(n_vars)]
-                    f = [run_normalised(vids[0]), run_normalised(vids[1]), run_normalised(vids[2])]
-                    f.append(torch.flip(f[0], dims=[1]))  # trev == reversed orig (dataset.py:201-207)
-                    feats = torch.stack(f, dim=1)
-                    for it in items:
-                        small.append(([it[v][1] for v in range(4)], [it[v][2] for v in range(4)],
-                                      [it[v][3] for v in range(4)], None))
-                else:
-                    feats = run_normalised(torch.stack([it[0] for it in items])).unsqueeze(1)
-                    for it in items:
-                        small.append(([it[1]], [it[2]], [it[3]], it[4]))
-        feats = feats.to(feat_dtype)
+        feats, small = extract_clips(ids)
         all_feats = gather_rows(feats.contiguous(), g1 - g0, dst=0)
         if world > 1:
             import torch.distributed as dist
@@ -280,12 +338,7 @@ def main(argv=None):
         if is_main:
             host = all_feats.cpu()
             for k in range(g1 - g0):
-                clip = ds.index[g0 + k]
-                j3s, j2s, Ks, box = small_all[k]
-                metas = [{"subject": clip.subject, "action": clip.action, "cam": clip.cam, "start": clip.start,
-                          "end": clip.end, "aug": AUG_NAMES[v] if args.augment else "orig",
-                          "box": box if not args.augment else None} for v in range(n_vars)]
-                writer.add(ClipRecord([host[k, v] for v in range(n_vars)], j3s, j2s, Ks, metas))
+                writer.add(clip_record(g0 + k, host[k], small_all[k]))
             done = g1
             if done % 200 < B * world or done == n_clips:
                 dt = time.time() - t_last

@@ -57,17 +57,21 @@ def test_b200_backend_refuses_to_run_without_cuda(tmp_path):
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
-def test_torch_backend_one_vs_two_processes(tmp_path):
-    """Reference-path run on CPU; the same job split over 2 ranks (gloo) writes the same shards.  (oneDNN picks
-    batch-size-dependent kernels, so the torch backend is only equal to fp32 rounding across splits; the b200
-    backend is bit-identical — tests/test_entrypoint.py::test_b200_backend_two_ranks_equal_one.)"""
+@pytest.mark.parametrize("mode", ["sharded", "gather"])
+def test_torch_backend_one_vs_two_processes(tmp_path, mode):
+    """Reference-path run on CPU; the same job split over 2 ranks (gloo) writes the same shards, with the
+    shard-parallel writer (every rank writes the shards it owns, no gather: the default) and with the gather-to-rank-0
+    writer.  (oneDNN picks batch-size-dependent kernels, so the torch backend is only equal to fp32 rounding across
+    splits; the b200 backend is bit-identical — tests/test_entrypoint.py::test_b200_backend_two_ranks_equal_one.)"""
     a, b = str(tmp_path / "w1"), str(tmp_path / "w2")
     base = ["--synthetic", "10:240x260:230", "--backend", "torch", "--device", "cpu"] + COMMON
     out = run(base + ["--out", a])
     assert "packed into 3 shard(s)" in out
-    run(base + ["--out", b], nproc=2)
+    out2 = run(base + ["--out", b, "--multi-gpu-writer", mode], nproc=2, port=29533 if mode == "sharded" else 29534)
+    assert ("by 2 ranks" in out2) == (mode == "sharded")
     ia, sa = load_root(a)
     ib, sb = load_root(b)
+    assert ia == ib
     assert ia["clips"] == ib["clips"] and ia["n_shards"] == ib["n_shards"] == 3 and ia["seq_len"] == 4
     for x, y in zip(sa, sb):
         for k in ("joints3d", "joints2d", "K"):
@@ -142,9 +146,14 @@ def test_b200_backend_two_ranks_equal_one(tmp_path):
     a, b = str(tmp_path / "g1"), str(tmp_path / "g2")
     base = ["--synthetic", "12:224x224", "--backend", "b200"] + COMMON
     run(base + ["--out", a])
-    run(base + ["--out", b], nproc=2, port=29544)
-    ia, sa = load_root(a)
-    ib, sb = load_root(b)
-    assert ia["clips"] == ib["clips"]
-    for x, y in zip(sa, sb):
-        assert torch.equal(x["feats"], y["feats"])
+    for mode, port in (("sharded", 29544), ("gather", 29545)):
+        b = str(tmp_path / f"g2_{mode}")
+        run(base + ["--out", b, "--multi-gpu-writer", mode], nproc=2, port=port)
+        ia, sa = load_root(a)
+        ib, sb = load_root(b)
+        assert ia == ib
+        for x, y in zip(sa, sb):
+            assert torch.equal(x["feats"], y["feats"])
+            for k in ("joints3d", "joints2d", "K"):
+                assert torch.equal(x[k], y[k]), k
+            assert [m["start"] for m in x["meta"]] == [m["start"] for m in y["meta"]]

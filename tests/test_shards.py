@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from conftest import REFERENCE_SRC
-from phdfx.shards import AUG_NAMES, AsyncShardWriter, ClipRecord, ShardWriter
+from phdfx.shards import (AUG_NAMES, AsyncShardWriter, ClipRecord, ShardWriter, assemble_shard, index_from_plan,
+                          plan_shards, shard_path)
 
 HAVE_REF = os.path.isdir(REFERENCE_SRC)
 
@@ -171,3 +172,57 @@ def test_reference_reader_and_sampler_consume_our_output(tmp_path):
     assert batches and all(len(b) == 8 for b in batches)
     ds_test = Human36MFeatureClips(root=str(tmp_path), subjects=[6], test_set=True)
     assert all(ds_test[i][4]["subject"] == 6 for i in range(len(ds_test)))
+
+
+# ---------------------------------------------------------------------------------------------- shard plan
+@pytest.mark.parametrize("n_clips,shard_size,pool", [(0, 4, 8), (1, 4, 8), (3, 4, 8), (8, 4, 8), (23, 5, 8), (23, 5, 7),
+                                                      (40, 4, 6), (64, 8, 8), (100, 7, 1000), (57, 1, 3)])
+def test_plan_shards_is_the_streaming_writers_permutation(tmp_path, n_clips, shard_size, pool):
+    """plan_shards (integers only) predicts exactly which clip the streaming writer — itself byte-identical to the
+    reference's functions (test_identical_to_reference_writer) — puts in which row of which shard."""
+    recs = make_records(n_clips, 1)
+    for i, r in enumerate(recs):
+        r.metas[0]["start"] = i  # tag every record with its arrival number
+    index = write(tmp_path, recs, 1, shard_size=shard_size, pool=pool, seed=77)
+    plan = plan_shards(n_clips, shard_size, pool, 77)
+    assert len(plan) == index["n_shards"] and sum(len(p) for p in plan) == n_clips
+    assert sorted(i for p in plan for i in p) == list(range(n_clips))
+    for sid, ids in enumerate(plan):
+        shard = torch.load(tmp_path / f"shard_{sid:05d}.pt", weights_only=True)
+        assert [m["start"] for m in shard["meta"]] == ids
+    assert [(c["shard_id"], c["row"], c["start"]) for c in index["clips"]] == \
+        [(sid, row, i) for sid, ids in enumerate(plan) for row, i in enumerate(ids)]
+
+
+@pytest.mark.parametrize("n_vars", [1, 4])
+def test_planned_writing_equals_streaming(tmp_path, n_vars):
+    """Shards assembled rank by rank from the plan (any order, any owner) + index_from_plan == what the one-process
+    streaming writer puts on disk: same index, same tensors bit for bit, same meta lists, same pickle format.  (The
+    raw bytes of legacy torch pickles embed storage keys derived from memory addresses, so they are not comparable.)"""
+    recs = make_records(29, n_vars, seed=3)
+    a, b = tmp_path / "stream", tmp_path / "planned"
+    index = write(a, recs, n_vars, shard_size=6, pool=10, seed=5)
+    b.mkdir()
+    plan = plan_shards(29, 6, 10, 5)
+    w = AsyncShardWriter()
+    for rank in (1, 0, 2):  # three "ranks", out of order
+        for sid in range(rank, len(plan), 3):
+            w.save(assemble_shard([recs[i] for i in plan[sid]], n_vars), shard_path(b, sid))
+    w.wait()
+    w.stop()
+    idx = index_from_plan(plan, lambda i: recs[i].metas[0], n_vars, seq_len=6, frame_skip=2, save_fp16=False,
+                          augment=n_vars > 1, shuffle_seed=5, shuffle_pool=10)
+    assert idx == index
+    for sid in range(len(plan)):
+        x = torch.load(a / f"shard_{sid:05d}.pt", weights_only=True)
+        y = torch.load(b / f"shard_{sid:05d}.pt", weights_only=True)
+        assert x.keys() == y.keys() and x["n_vars"] == y["n_vars"] == n_vars
+        for k in ("feats", "joints3d", "joints2d", "K"):
+            assert x[k].dtype == y[k].dtype and torch.equal(x[k], y[k]), k
+        assert len(x["meta"]) == len(y["meta"])
+        for mx, my in zip(x["meta"], y["meta"]):
+            assert {k: v for k, v in mx.items() if k != "box"} == {k: v for k, v in my.items() if k != "box"}
+            assert (mx["box"] is None and my["box"] is None) or torch.equal(mx["box"], my["box"])
+        assert (a / f"shard_{sid:05d}.pt").stat().st_size == (b / f"shard_{sid:05d}.pt").stat().st_size
+        with open(b / f"shard_{sid:05d}.pt", "rb") as f:
+            assert f.read(2) != b"PK"  # legacy (non-zip) pickle, like the reference (:45)
