@@ -284,7 +284,9 @@ class ExtractGraph:
             eng.extract_u8(frames, boxes, flip_w=flip_w, out=self.out)
         torch.cuda.current_stream(eng.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other host threads (a DataLoader's pin-memory thread calling cudaHostAlloc, a shard writer) may
+        # make CUDA calls while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             eng.extract_u8(frames, boxes, flip_w=flip_w, out=self.out)
         self.launches = eng.launches
 
@@ -303,7 +305,7 @@ class CapturedCall:
             fn()
         torch.cuda.current_stream(eng.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.result = fn()
 
     def replay(self):

@@ -62,8 +62,9 @@ def parse_args(argv=None):
     # --- additions ---
     p.add_argument("--backend", choices=["b200", "torch"], default="b200",
                    help="b200: libphdfx.so (no fallback); torch: the reference's eager path (for comparison runs)")
-    p.add_argument("--synthetic", type=str, default=None, metavar="N[:HxW[:SIDE]]",
-                   help="use N synthetic clips of HxW uint8 frames (person box side SIDE) instead of --root")
+    p.add_argument("--synthetic", type=str, default=None, metavar="N[:HxW[:SIDE[:fast]]]",
+                   help="use N synthetic clips of HxW uint8 frames (person box side SIDE, 0 = whole frame) instead of "
+                        "--root; ':fast' derives every clip from one random base clip (throughput runs)")
     p.add_argument("--weights", type=str, default="imagenet",
                    help="'imagenet' (torchvision IMAGENET1K_V2, needs network/cache), 'random:SEED', or a state_dict path")
     p.add_argument("--dataset-path", type=str, default=None, help="directory holding the user's dataset.py")
@@ -131,10 +132,11 @@ def parse_synthetic(spec: str, args):
         h, w = (int(v) for v in parts[1].lower().split("x"))
     if len(parts) > 2:
         side = int(parts[2])
+    fast = len(parts) > 3 and parts[3] == "fast"
     if args.max_clips is not None:
         n = min(n, args.max_clips)
     return SyntheticH36MClips(n, seq_len=args.seq_len, height=h, width=w, subjects=tuple(args.subjects), seed=0,
-                              box_side=side)
+                              box_side=side, fast=fast)
 
 
 @torch.no_grad()
@@ -174,8 +176,11 @@ def main(argv=None):
 
         frames_per_call = args.batch_size * T
         backbone = phdfx.B200Backbone(torch_backbone, device=device, max_frames=min(frames_per_call, 1280))
+        # host uint8 frames -> host features: pinned, double-buffered H2D / compute / D2H (phdfx/stream.py)
+        streamer = phdfx.StreamingExtractor(backbone, batch=min(256, backbone.max_frames))
     else:
         backbone = torch_backbone.to(device)
+        streamer = None
     feat_dtype = torch.float16 if args.save_fp16 else torch.float32
 
     def run_normalised(v_video: torch.Tensor) -> torch.Tensor:
@@ -188,8 +193,9 @@ def main(argv=None):
                 return backbone(x).flatten(1).view(Bv, Tt, -1).float()
         return backbone(x).flatten(1).view(Bv, Tt, -1)
 
-    def run_u8(frames: torch.Tensor, boxes: torch.Tensor, flip: bool) -> torch.Tensor:
-        """Seam B: (Bv,T,H,W,3) uint8 + per-clip boxes -> (Bv,T,2048) on the device."""
+    def run_u8(frames: torch.Tensor, boxes: torch.Tensor, flip: bool, to_host: bool = False) -> torch.Tensor:
+        """Seam B: (Bv,T,H,W,3) uint8 + per-clip boxes -> (Bv,T,2048) on the device (to_host: in pinned host memory,
+        through the streaming extractor)."""
         Bv, Tt, H, W, _ = frames.shape
         if args.backend == "torch":
             # the reference's own front end (src/dataset.py:141-152, :166, :242-245), clip by clip
@@ -206,9 +212,11 @@ def main(argv=None):
                     v = torch.flip(v, dims=[-1])
                 vids.append((v - mean) / std)
             return run_normalised(torch.stack(vids))
+        bx = boxes.to(torch.int32).repeat_interleave(Tt, dim=0)
+        if to_host:  # overlapped copies, features land in pinned host memory
+            return streamer(frames.view(Bv * Tt, H, W, 3), bx, flip_w=flip).view(Bv, Tt, -1)
         fr = frames.view(Bv * Tt, H, W, 3).to(device, non_blocking=True)
-        bx = boxes.to(torch.int32).repeat_interleave(Tt, dim=0).to(device, non_blocking=True)
-        return backbone.extract_u8(fr, bx, flip_w=flip).view(Bv, Tt, -1)
+        return backbone.extract_u8(fr, bx.to(device, non_blocking=True), flip_w=flip).view(Bv, Tt, -1)
 
     def jitter_variant(frames: torch.Tensor, boxes: torch.Tensor, clip_ids) -> torch.Tensor:
         """Colour-jitter variant in synthetic mode: the reference's recipe (src/dataset.py:188-198: ColorJitter on
@@ -230,27 +238,29 @@ def main(argv=None):
             outs.append((vid - mean) / std)
         return run_normalised(torch.stack(outs))
 
-    def extract_clips(ids):
-        """Features + annotations of the clips `ids` (dataset numbers):
-        (feats [len(ids), n_vars, T, 2048] on the device in feat_dtype, [(joints3d[v], joints2d[v], K[v], box)])."""
-        feats = torch.empty(0, n_vars, T, 2048, device=device)
+    def extract_clips(ids, items, to_host: bool = False):
+        """Features + annotations of the clips `ids` (dataset numbers; `items` = what the dataset returned for them,
+        synthetic clips already collated): (feats [len(ids), n_vars, T, 2048] in feat_dtype — on the device, or on the
+        host when to_host —, [(joints3d[v], joints2d[v], K[v], box)])."""
+        feats = torch.empty(0, n_vars, T, 2048, device="cpu" if to_host else device)
         small = []  # per clip: (joints3d[v], joints2d[v], K[v], box)
         if not ids:
             return feats.to(feat_dtype), small
-        items = [ds[i] for i in ids] if synthetic or args.num_workers == 0 else _loader_fetch(ds, ids, args)
         if synthetic:
-            frames = torch.stack([it[0] for it in items])
-            boxes = torch.stack([it[4] for it in items])
-            f_orig = run_u8(frames, boxes, False)
+            frames, boxes, items = items  # (Bv,T,H,W,3) uint8, (Bv,4), per-clip tuples without the frames
+            host = to_host and args.backend == "b200"
+            f_orig = run_u8(frames, boxes, False, to_host=host)
             if args.augment:
                 f_jit = jitter_variant(frames, boxes, ids)
-                f_flip = run_u8(frames, boxes, True)
+                f_flip = run_u8(frames, boxes, True, to_host=host)
+                if host:
+                    f_jit = f_jit.cpu()
                 f_trev = torch.flip(f_orig, dims=[1])  # frames are independent: exact (SURVEY.md 8f N1)
                 feats = torch.stack([f_orig, f_jit, f_flip, f_trev], dim=1)
             else:
                 feats = f_orig.unsqueeze(1)
             for it in items:
-                j3, j2, K, box = it[1], it[2], it[3], it[4]
+                j3, j2, K, box = it
                 if args.augment:
                     small.append(_augment_annotations(j3, j2, K))
                 else:
@@ -268,7 +278,24 @@ def main(argv=None):
                 feats = run_normalised(torch.stack([it[0] for it in items])).unsqueeze(1)
                 for it in items:
                     small.append(([it[1]], [it[2]], [it[3]], it[4]))
-        return feats.to(feat_dtype), small
+        feats = feats.to(feat_dtype)
+        return (feats.cpu() if to_host else feats), small
+
+    def clip_batches(batches):
+        """(ids, items) for every id list in `batches`, in order.  With --num-workers > 0 one persistent DataLoader
+        decodes / generates the clips of batch i+1.. in worker processes (pinned) while batch i is on the GPU — the
+        reference's worker pool (:195-204), driven by an explicit batch list instead of a sequential sampler."""
+        live = [b for b in batches if b]
+        if args.num_workers > 0 and live:
+            from torch.utils.data import DataLoader
+
+            loader = iter(DataLoader(ds, batch_sampler=live, num_workers=min(args.num_workers, len(live)),
+                                     collate_fn=_collate_synthetic if synthetic else _collate_list,
+                                     pin_memory=torch.cuda.is_available(), prefetch_factor=2))
+        else:
+            loader = ((_collate_synthetic if synthetic else _collate_list)([ds[i] for i in b]) for b in live)
+        for b in batches:
+            yield b, (next(loader) if b else None)
 
     def clip_record(i, host_feats, small_i):
         """ClipRecord of dataset clip i: host_feats [n_vars, T, 2048], small_i as returned by extract_clips."""
@@ -288,13 +315,14 @@ def main(argv=None):
         plan = plan_shards(n_clips, args.shard_size, args.shuffle_pool, args.shuffle_seed)
         aw = AsyncShardWriter()
         mine = list(range(rank, len(plan), world))
+        parts = [(sid, plan[sid][c0:c0 + B]) for sid in mine for c0 in range(0, len(plan[sid]), B)]
+        fetched = clip_batches([p for _, p in parts])
         for k, sid in enumerate(mine):
             ids = plan[sid]
             groups = []
-            for c0 in range(0, len(ids), B):
-                part = ids[c0:c0 + B]
-                feats, small = extract_clips(part)
-                host = feats.cpu()
+            while len(groups) < len(ids):
+                part, items = next(fetched)
+                host, small = extract_clips(part, items, to_host=True)
                 groups.extend(clip_record(i, host[j], small[j]) for j, i in enumerate(part))
             aw.save(assemble_shard(groups, n_vars), shard_path(out_root, sid))
             log(f"[{100 * (k + 1) / max(1, len(mine)):5.1f}%] rank 0: shard {sid} ({len(ids)} clips) queued "
@@ -321,11 +349,16 @@ def main(argv=None):
     # rank 0 can append clips to the shuffle pool in the reference's order after every gather
     t_last = t_all
     done = 0
-    for g0 in range(0, n_clips, B * world):
+    starts = list(range(0, n_clips, B * world))
+    my_ids = []
+    for g0 in starts:
+        lo, hi = shard_range(min(n_clips, g0 + B * world) - g0, rank, world)
+        my_ids.append(list(range(g0 + lo, g0 + hi)))
+    fetched = clip_batches(my_ids)
+    for g0 in starts:
         g1 = min(n_clips, g0 + B * world)
-        lo, hi = shard_range(g1 - g0, rank, world)
-        ids = list(range(g0 + lo, g0 + hi))
-        feats, small = extract_clips(ids)
+        ids, items = next(fetched)
+        feats, small = extract_clips(ids, items, to_host=world == 1)
         all_feats = gather_rows(feats.contiguous(), g1 - g0, dst=0)
         if world > 1:
             import torch.distributed as dist
@@ -374,13 +407,15 @@ def _augment_annotations(j3, j2, K):
     return ([j3, j3, j3f, torch.flip(j3, dims=[0])], [j2, j2, j2f, torch.flip(j2, dims=[0])], [K, K, Kf, K], None)
 
 
-def _loader_fetch(ds, ids, args):
-    """Decode a list of clips with DataLoader workers (the reference's :195-204 worker pool, per global batch)."""
-    from torch.utils.data import DataLoader, Subset
+def _collate_list(batch):
+    """Real-dataset clips stay a list of per-clip items (src/dataset.py:403-437 return types)."""
+    return batch
 
-    loader = DataLoader(Subset(ds, ids), batch_size=1, shuffle=False, num_workers=min(args.num_workers, len(ids)),
-                        collate_fn=lambda b: b[0])
-    return list(loader)
+
+def _collate_synthetic(batch):
+    """Synthetic clips: stack the uint8 frames and boxes in the worker, keep the small annotations per clip."""
+    return (torch.stack([it[0] for it in batch]), torch.stack([it[4] for it in batch]),
+            [(it[1], it[2], it[3], it[4]) for it in batch])
 
 
 if __name__ == "__main__":
