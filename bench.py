@@ -195,6 +195,9 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from phdfx.dist import bind_to_gpu_numa
+
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 else None  # pinned host buffers on the GPU's own socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -341,7 +344,8 @@ def run_b200(args):
                                       + (", final NCCL gather of features inside the timed region" if world > 1 else "")},
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d / steps_e2e),
                     "d2h_bytes_per_step": int(d2h / steps_e2e),
-                    "api": "phdfx.StreamingExtractor (pinned host uint8 -> features in pinned host fp32)"},
+                    "api": "phdfx.StreamingExtractor (pinned host uint8 -> features in pinned host fp32)",
+                    "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved_tf / pk["bf16_sustained"],

@@ -102,6 +102,9 @@ def dist_setup():
 
         backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            from phdfx.dist import bind_to_gpu_numa
+
+            bind_to_gpu_numa(local)  # before any pinned allocation: host buffers on the GPU's own socket
             torch.cuda.set_device(local)
             dist.init_process_group(backend, device_id=torch.device("cuda", local))
         else:
