@@ -1,3 +1,13 @@
+"""Experiment: how a layer's time changes when every persistent grid runs on fewer SMs (PHDFX_SM_CAP=n, read at
+phdfx_create).  A layer bound by something every SM owns privately (tensor pipe, shared memory, its L2 port) slows down
+in proportion to the SMs taken away; one bound by a shared resource (HBM, aggregate L2 bandwidth) does not.
+
+    for c in 148 110 74 36; do PHDFX_SM_CAP=$c python tools/exp_sm_cap.py; done
+
+Measured on the v8 build (B200, batch 256, L2 flushed): layer3.1.conv3 0.051 / 0.059 / 0.074 / 0.129 ms at
+148 / 110 / 74 / 36 SMs, layer3.1.conv2 (tensor-bound 3x3) 0.051 / 0.062 / 0.082 / 0.133 — half the SMs cost 1.4-1.6x,
+not 2x: at 148 SMs both are partly limited by what the SMs share (aggregate L2 -> SM operand bandwidth).
+"""
 import os, sys, json
 sys.path.insert(0, "implementation-phd-lab-vision_b200"); sys.path.insert(0, "oracle")
 import torch, phdfx, resnet50_ref as R
