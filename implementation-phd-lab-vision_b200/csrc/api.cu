@@ -56,6 +56,7 @@ struct phdfx {
   std::vector<void*> bufs;          // arena buffers by id
   std::vector<size_t> buf_bytes;    // per-frame bytes of each arena buffer
   int last_launches = 0;
+  float* d_row_sums = nullptr;      // colour-jitter scratch: one grey-level sum per output row, [max_frames][224]
   bool use_chain = true;            // PHDFX_NO_CHAIN=1 at phdfx_create: keep layer1 on the per-conv kernels
   std::vector<ChainPlan> chains;
   std::vector<int> chain_at;        // per layer: index into `chains` of the chain STARTING there, else -1
@@ -589,6 +590,8 @@ void free_device_state(phdfx_t* h) {
   h->buf_bytes.clear();
   if (h->d_weights) cudaFree(h->d_weights);
   if (h->d_bias) cudaFree(h->d_bias);
+  if (h->d_row_sums) cudaFree(h->d_row_sums);
+  h->d_row_sums = nullptr;
   h->d_weights = nullptr;
   h->d_bias = nullptr;
   h->layers.clear();
@@ -708,6 +711,7 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
     CUDA_TRY(h, cudaMalloc(&h->bufs[i], h->buf_bytes[i] * h->max_frames + 65536));
     CUDA_TRY(h, cudaMemset(h->bufs[i], 0, h->buf_bytes[i] * h->max_frames + 65536));
   }
+  CUDA_TRY(h, cudaMalloc(&h->d_row_sums, static_cast<size_t>(h->max_frames) * kImg * sizeof(float)));
   h->maps.assign(n_layers, LayerMaps());
   for (int i = 0; i < n_layers; ++i) {
     const auto& L = h->layers[i];
@@ -755,8 +759,8 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
   return 0;
 }
 
-int phdfx_preprocess_u8(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const int32_t* d_boxes,
-                        int flip_w, void* d_out, void* stream) {
+static int preprocess_impl(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const int32_t* d_boxes,
+                           int flip_w, const float* d_jitter, void* d_out, void* stream) {
   if (int rc = check_ready(h, n)) return rc;
   if (!d_frames || H < 1 || W < 1) return fail(h, PHDFX_ERR_INVALID, "phdfx_preprocess_u8: bad frames/H/W");
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -765,16 +769,44 @@ int phdfx_preprocess_u8(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W
   const size_t k1_row_cap = (static_cast<size_t>(W) * 3 + 32 + 15) & ~static_cast<size_t>(15);
   const size_t k1_smem = kK1LutBytes + kK1Warps * 2 * k1_row_cap;
   if (k1_smem > 200 * 1024) return fail(h, PHDFX_ERR_INVALID, "frame width %d too large for the preprocess kernel", W);
-  if (k1_smem > 48 * 1024)
-    CUDA_TRY(h, cudaFuncSetAttribute(preprocess_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(k1_smem)));
   const int k1_blocks = (n * kImg + kK1Warps - 1) / kK1Warps;
   const int k1_cap = h->num_sms * 16;
-  CUDA_TRY(h, launch_pdl(preprocess_u8_kernel, dim3(k1_blocks < k1_cap ? k1_blocks : k1_cap), dim3(kK1Warps * 32),
-                         k1_smem, static_cast<cudaStream_t>(stream), d_frames, n, H, W, d_boxes, flip_w,
-                         static_cast<__nv_bfloat16*>(out)));
-  h->last_launches++;
+  const dim3 grid(k1_blocks < k1_cap ? k1_blocks : k1_cap), block(kK1Warps * 32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (!d_jitter) {
+    if (k1_smem > 48 * 1024)
+      CUDA_TRY(h, cudaFuncSetAttribute(preprocess_u8_kernel<KIND_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(k1_smem)));
+    CUDA_TRY(h, launch_pdl(preprocess_u8_kernel<KIND_PLAIN>, grid, block, k1_smem, st, d_frames, n, H, W, d_boxes,
+                           flip_w, o, static_cast<const float*>(nullptr), static_cast<float*>(nullptr)));
+    h->last_launches++;
+    return 0;
+  }
+  // colour jitter: grey-level row sums of the image in front of the contrast op, then the full pipeline
+  if (k1_smem > 48 * 1024) {
+    CUDA_TRY(h, cudaFuncSetAttribute(preprocess_u8_kernel<KIND_JITTER_SUMS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(k1_smem)));
+    CUDA_TRY(h, cudaFuncSetAttribute(preprocess_u8_kernel<KIND_JITTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(k1_smem)));
+  }
+  CUDA_TRY(h, launch_pdl(preprocess_u8_kernel<KIND_JITTER_SUMS>, grid, block, k1_smem, st, d_frames, n, H, W, d_boxes,
+                         flip_w, o, d_jitter, h->d_row_sums));
+  CUDA_TRY(h, launch_pdl(preprocess_u8_kernel<KIND_JITTER>, grid, block, k1_smem, st, d_frames, n, H, W, d_boxes,
+                         flip_w, o, d_jitter, h->d_row_sums));
+  h->last_launches += 2;
   return 0;
+}
+
+int phdfx_preprocess_u8(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const int32_t* d_boxes,
+                        int flip_w, void* d_out, void* stream) {
+  return preprocess_impl(h, d_frames, n, H, W, d_boxes, flip_w, nullptr, d_out, stream);
+}
+
+int phdfx_preprocess_u8_jitter(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const int32_t* d_boxes,
+                               int flip_w, const float* d_jitter, void* d_out, void* stream) {
+  if (!d_jitter) return fail(h, PHDFX_ERR_INVALID, "phdfx_preprocess_u8_jitter: null jitter parameters");
+  return preprocess_impl(h, d_frames, n, H, W, d_boxes, flip_w, d_jitter, d_out, stream);
 }
 
 int phdfx_nchw_f32_to_nhwc_bf16(phdfx_t* h, const float* d_x, int n, void* d_out, void* stream) {
@@ -875,6 +907,12 @@ int phdfx_forward_timed(phdfx_t* h, const void* d_in, int n, float* d_feats, voi
 int phdfx_extract_u8(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const int32_t* d_boxes, int flip_w,
                      float* d_feats, void* stream) {
   if (int rc = phdfx_preprocess_u8(h, d_frames, n, H, W, d_boxes, flip_w, nullptr, stream)) return rc;
+  return forward_impl(h, nullptr, n, d_feats, static_cast<cudaStream_t>(stream));
+}
+
+int phdfx_extract_u8_jitter(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const int32_t* d_boxes,
+                            int flip_w, const float* d_jitter, float* d_feats, void* stream) {
+  if (int rc = phdfx_preprocess_u8_jitter(h, d_frames, n, H, W, d_boxes, flip_w, d_jitter, nullptr, stream)) return rc;
   return forward_impl(h, nullptr, n, d_feats, static_cast<cudaStream_t>(stream));
 }
 

@@ -33,9 +33,91 @@ constexpr int kStemLeftPad = 4;
 constexpr int kK1Warps = 8;
 constexpr int kK1LutBytes = 3 * 256 * 2;
 
+// ---- colour jitter (the reference's `cjitter` variant, src/dataset.py:188-198: torchvision v2 ColorJitter on the
+// resized [0,1] clip, one parameter draw per clip, before Normalize).  Parameters arrive per FRAME as 12 floats:
+//   [0..3] the four ops in application order (0 brightness, 1 contrast, 2 saturation, 3 hue; transforms/v2/_color.py
+//   :156-173), [4] brightness factor, [5] contrast factor, [6] float32(1.0 - contrast) (formed in double, as
+//   _blend's `alpha`, functional/_color.py:92-97), [7] saturation factor, [8] float32(1.0 - saturation), [9] hue.
+// Every op is the fp32 arithmetic of torchvision transforms/v2/functional/_color.py (:31-48 grey, :112-123 brightness,
+// :149-165 saturation, :188-205 contrast, :300-395 hue); oracle/preprocess_ref.py restates the same and is pinned
+// against torchvision to 1e-6.  Contrast blends with the frame's mean grey level of the image AS IT IS when the op
+// runs, so the kernel runs twice: KIND_JITTER_SUMS applies the ops that precede contrast and writes one fp32 sum of
+// grey per output row; KIND_JITTER adds the 224 row sums (in double, fixed order) and finishes.
+constexpr int kJitterFloats = 12;
+enum K1Kind : int { KIND_PLAIN = 0, KIND_JITTER_SUMS = 1, KIND_JITTER = 2 };
+
+__device__ __forceinline__ float jit_clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+__device__ __forceinline__ float jit_gray(const float (&c)[3]) {
+  return __fmaf_rn(c[2], 0.114f, __fmaf_rn(c[1], 0.587f, __fmul_rn(c[0], 0.2989f)));
+}
+__device__ __forceinline__ void jit_blend(float (&c)[3], float other, float ratio, float rest) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c[k] = jit_clamp01(__fmaf_rn(other, rest, __fmul_rn(c[k], ratio)));
+}
+__device__ __forceinline__ void jit_hue(float (&c)[3], float hue) {
+  const float r = c[0], g = c[1], b = c[2];
+  const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
+  const bool eqc = maxc == minc;
+  const float cr = __fsub_rn(maxc, minc);
+  const float s = __fdiv_rn(cr, eqc ? 1.0f : maxc);
+  const float div = eqc ? 1.0f : cr;
+  const float rc = __fdiv_rn(__fsub_rn(maxc, r), div), gc = __fdiv_rn(__fsub_rn(maxc, g), div),
+              bc = __fdiv_rn(__fsub_rn(maxc, b), div);
+  const bool neq_r = maxc != r, eq_g = maxc == g;
+  const float hg = (eq_g && neq_r) ? __fsub_rn(__fadd_rn(rc, 2.0f), bc) : 0.0f;
+  const float hr = (!neq_r) ? __fsub_rn(bc, gc) : 0.0f;
+  const float hb = (neq_r && !eq_g) ? __fsub_rn(__fadd_rn(gc, 4.0f), rc) : 0.0f;
+  float h = __fadd_rn(__fadd_rn(hr, hg), hb);
+  h = fmodf(__fadd_rn(__fmul_rn(h, 1.0f / 6.0f), 1.0f), 1.0f);
+  h = __fadd_rn(h, hue);              // h.add_(hue_factor).remainder_(1.0): result takes the divisor's sign
+  h = __fsub_rn(h, floorf(h));
+  if (h >= 1.0f) h = 0.0f;
+  const float v = maxc;
+  const float h6 = __fmul_rn(h, 6.0f);
+  const float fi = floorf(h6);
+  const float f = __fsub_rn(h6, fi);
+  int i = static_cast<int>(fi) % 6;
+  if (i < 0) i += 6;
+  const float sxf = __fmul_rn(s, f);
+  const float oms = __fsub_rn(1.0f, s);
+  const float q = jit_clamp01(__fmul_rn(__fsub_rn(1.0f, sxf), v));
+  const float t = jit_clamp01(__fmul_rn(__fadd_rn(sxf, oms), v));
+  const float pp = jit_clamp01(__fmul_rn(oms, v));
+  // vpqt -> rgb by sextant (functional/_color.py:359)
+  switch (i) {
+    case 0: c[0] = v, c[1] = t, c[2] = pp; break;
+    case 1: c[0] = q, c[1] = v, c[2] = pp; break;
+    case 2: c[0] = pp, c[1] = v, c[2] = t; break;
+    case 3: c[0] = pp, c[1] = q, c[2] = v; break;
+    case 4: c[0] = t, c[1] = pp, c[2] = v; break;
+    default: c[0] = v, c[1] = pp, c[2] = q; break;
+  }
+}
+// the ops of one frame in order; until_contrast: stop in front of the contrast op (first pass)
+__device__ __forceinline__ void jit_apply(float (&c)[3], const float* __restrict__ prm, float mean_gray,
+                                          bool until_contrast) {
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int op = static_cast<int>(prm[k]);
+    if (op == 0) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) c[j] = jit_clamp01(__fmul_rn(c[j], prm[4]));
+    } else if (op == 1) {
+      if (until_contrast) return;
+      jit_blend(c, mean_gray, prm[5], prm[6]);
+    } else if (op == 2) {
+      jit_blend(c, jit_gray(c), prm[7], prm[8]);
+    } else {
+      jit_hue(c, prm[9]);
+    }
+  }
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(kK1Warps * 32)
 preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
-                     const int32_t* __restrict__ boxes, int flip_w, __nv_bfloat16* __restrict__ out) {
+                     const int32_t* __restrict__ boxes, int flip_w, __nv_bfloat16* __restrict__ out,
+                     const float* __restrict__ jitter, float* __restrict__ row_sums) {
   extern __shared__ __align__(16) uint8_t s_rows[];
   griddep_launch_dependents();
   griddep_wait();  // the arena input buffer may still be read by the previous step's stem kernel
@@ -102,7 +184,17 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
     const float scale_w = __fdiv_rn(static_cast<float>(bw), static_cast<float>(kImg));
     // a 224x224 crop: F.resize returns its input untouched (torchvision transforms/functional.py:470-471); the stencil
     // below degenerates to weight 1 on v00 and +0 elsewhere, i.e. the same bytes — skip the arithmetic
-    const bool ident = (bh == kImg) && (bw == kImg);
+    const bool ident = (bh == kImg) && (bw == kImg) && KIND == KIND_PLAIN;
+    const float* prm = KIND != KIND_PLAIN ? jitter + static_cast<size_t>(n) * kJitterFloats : nullptr;
+    float mean_gray = 0.0f;
+    if (KIND == KIND_JITTER) {  // sum of the frame's 224 row sums, in double, fixed order
+      double acc = 0.0;
+      for (int r = lane; r < kImg; r += 32) acc += static_cast<double>(row_sums[static_cast<size_t>(n) * kImg + r]);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      mean_gray = static_cast<float>(acc / static_cast<double>(kImg * kImg));
+    }
+    float gray_sum = 0.0f;
     for (int wp = lane; wp < kStemWPad; wp += 32) {
       uint2 o = make_uint2(0u, 0u);
       int x = wp - kStemLeftPad;
@@ -124,7 +216,8 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
         const float lx0 = __fsub_rn(1.0f, lx1);
         const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1);
         const float w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
-        uint32_t r[3];
+        uint32_t r[3] = {0u, 0u, 0u};
+        float px[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float v00 = static_cast<float>(t0[x0 * 3 + c]);
@@ -133,12 +226,31 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
           const float v11 = static_cast<float>(t1[x1 * 3 + c]);
           const float v = __fmaf_rn(w11, v11, __fmaf_rn(w10, v10, __fmaf_rn(w00, v00, __fmul_rn(w01, v01))));
           const int u8 = static_cast<int>(fminf(fmaxf(rintf(v), 0.0f), 255.0f));  // round half to even, uint8 range
-          r[c] = reinterpret_cast<const uint16_t*>(lut)[c * 256 + u8];
+          if (KIND == KIND_PLAIN)
+            r[c] = reinterpret_cast<const uint16_t*>(lut)[c * 256 + u8];
+          else
+            px[c] = __fdiv_rn(static_cast<float>(u8), 255.0f);  // frames.to(float32) / 255.0
+        }
+        if (KIND == KIND_JITTER_SUMS) {
+          jit_apply(px, prm, 0.0f, true);
+          gray_sum += jit_gray(px);
+        } else if (KIND == KIND_JITTER) {
+          jit_apply(px, prm, mean_gray, false);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const __nv_bfloat16 hv = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(px[c], mean[c]), stdv[c]));
+            r[c] = *reinterpret_cast<const uint16_t*>(&hv);
+          }
         }
         o.x = r[0] | (r[1] << 16);
         o.y = r[2];
       }
-      reinterpret_cast<uint2*>(out)[static_cast<size_t>(rowi) * kStemWPad + wp] = o;
+      if (KIND != KIND_JITTER_SUMS) reinterpret_cast<uint2*>(out)[static_cast<size_t>(rowi) * kStemWPad + wp] = o;
+    }
+    if (KIND == KIND_JITTER_SUMS) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) gray_sum += __shfl_xor_sync(0xffffffffu, gray_sum, d);
+      if (lane == 0) row_sums[rowi] = gray_sum;
     }
   }
 }

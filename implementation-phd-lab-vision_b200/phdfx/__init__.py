@@ -6,8 +6,8 @@ Drop-in for the hot path of ferreiraluisa/implementation-phd-lab-vision:
 """
 from ._lib import EXPORTS, FEAT_DIM, IMG, IN_CPAD, IN_LPAD, IN_WPAD, LIB_PATH, LayerDesc, load  # noqa: F401
 from .weights import Plan, build_plan, fold_conv_bn, pack_conv, pack_stem, pack_stem_pool, randomize_bn_  # noqa: F401
-from .backbone import B200Backbone, ExtractGraph  # noqa: F401
+from .backbone import B200Backbone, ExtractGraph, jitter_params  # noqa: F401
 from .stream import StreamingExtractor  # noqa: F401
 
-__all__ = ["B200Backbone", "ExtractGraph", "StreamingExtractor", "build_plan", "fold_conv_bn", "pack_conv", "pack_stem", "pack_stem_pool", "randomize_bn_", "Plan", "load",
+__all__ = ["B200Backbone", "ExtractGraph", "jitter_params", "StreamingExtractor", "build_plan", "fold_conv_bn", "pack_conv", "pack_stem", "pack_stem_pool", "randomize_bn_", "Plan", "load",
            "LayerDesc", "EXPORTS", "LIB_PATH", "FEAT_DIM", "IMG", "IN_WPAD", "IN_LPAD", "IN_CPAD"]

@@ -19,6 +19,8 @@ EXPORTS = [
     "phdfx_destroy",
     "phdfx_load_weights",
     "phdfx_preprocess_u8",
+    "phdfx_preprocess_u8_jitter",
+    "phdfx_extract_u8_jitter",
     "phdfx_nchw_f32_to_nhwc_bf16",
     "phdfx_forward",
     "phdfx_forward_timed",
@@ -34,6 +36,7 @@ EXPORTS = [
 
 PHDFX_CONV, PHDFX_STEM, PHDFX_MAXPOOL, PHDFX_STEM_POOL = 0, 1, 2, 3
 IMG, IN_WPAD, IN_LPAD, IN_CPAD, FEAT_DIM = 224, 232, 4, 4, 2048
+JITTER_FLOATS = 12  # one row of phdfx_preprocess_u8_jitter's parameter array
 
 
 class LayerDesc(C.Structure):
@@ -94,6 +97,10 @@ def load() -> C.CDLL:
     lib.phdfx_load_weights.argtypes = [vp, vp, i64, vp, i64, C.POINTER(LayerDesc), i32]
     lib.phdfx_preprocess_u8.restype = i32
     lib.phdfx_preprocess_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp]
+    lib.phdfx_preprocess_u8_jitter.restype = i32
+    lib.phdfx_preprocess_u8_jitter.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]
+    lib.phdfx_extract_u8_jitter.restype = i32
+    lib.phdfx_extract_u8_jitter.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]
     lib.phdfx_nchw_f32_to_nhwc_bf16.restype = i32
     lib.phdfx_nchw_f32_to_nhwc_bf16.argtypes = [vp, vp, i32, vp, vp]
     lib.phdfx_forward.restype = i32

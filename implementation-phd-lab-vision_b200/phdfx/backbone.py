@@ -20,6 +20,16 @@ from . import _lib
 from .weights import Plan, build_plan
 
 
+def jitter_params(fn_idx, brightness: float, contrast: float, saturation: float, hue: float) -> torch.Tensor:
+    """One row of K1's colour-jitter parameters from what torchvision's v2 ColorJitter.make_params returns
+    (transforms/v2/_color.py:146-154: fn_idx = randperm(4), the four factors): fp32 [12]."""
+    order = [float(int(v)) for v in fn_idx]
+    if sorted(order) != [0.0, 1.0, 2.0, 3.0]:
+        raise ValueError(f"fn_idx must be a permutation of 0..3, got {list(fn_idx)}")
+    b, c, s, h = float(brightness), float(contrast), float(saturation), float(hue)
+    return torch.tensor(order + [b, c, 1.0 - c, s, 1.0 - s, h, 0.0, 0.0], dtype=torch.float64).to(torch.float32)
+
+
 class B200Backbone:
     FEAT_DIM = _lib.FEAT_DIM
 
@@ -102,8 +112,9 @@ class B200Backbone:
     # ---- Seam B ---------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def extract_u8(self, frames: torch.Tensor, boxes: Optional[torch.Tensor] = None, flip_w: bool = False,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """frames: uint8 [N,H,W,3] on the device; boxes: int32 [N,4] (top,left,h,w) or None -> fp32 [N,2048]."""
+                   out: Optional[torch.Tensor] = None, jitter: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames: uint8 [N,H,W,3] on the device; boxes: int32 [N,4] (top,left,h,w) or None -> fp32 [N,2048].
+        jitter: fp32 [N,12] on the device (see jitter_params / include/phdfx.h): the reference's colour-jitter variant."""
         if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
             raise RuntimeError(f"expected uint8 [N,H,W,3], got {frames.dtype} {tuple(frames.shape)}")
         self._check_dev(frames, "frames")
@@ -117,14 +128,21 @@ class B200Backbone:
             if out.dtype != torch.float32 or tuple(out.shape) != (n, self.FEAT_DIM):
                 raise RuntimeError("out must be fp32 [N,2048]")
             self._check_dev(out, "out")
+        if jitter is not None:
+            self._check_jitter(jitter, n)
         launches = 0
         with torch.cuda.device(self.device):
             for i in range(0, n, self.max_frames):
                 m = min(self.max_frames, n - i)
                 bp = boxes[i:i + m].data_ptr() if boxes is not None else None
-                _lib.check(
-                    self._lib.phdfx_extract_u8(self._h, frames[i:i + m].data_ptr(), m, H, W, bp, int(flip_w),
-                                               feats[i:i + m].data_ptr(), self._stream()), self._h)
+                if jitter is None:
+                    rc = self._lib.phdfx_extract_u8(self._h, frames[i:i + m].data_ptr(), m, H, W, bp, int(flip_w),
+                                                    feats[i:i + m].data_ptr(), self._stream())
+                else:
+                    rc = self._lib.phdfx_extract_u8_jitter(self._h, frames[i:i + m].data_ptr(), m, H, W, bp,
+                                                           int(flip_w), jitter[i:i + m].data_ptr(),
+                                                           feats[i:i + m].data_ptr(), self._stream())
+                _lib.check(rc, self._h)
                 launches += self.last_launch_count
         self.launches = launches
         return feats
@@ -138,10 +156,17 @@ class B200Backbone:
         """Capture extract_u8 on exactly these tensors into a CUDA graph (54 launches -> one graph launch)."""
         return ExtractGraph(self, frames, boxes, flip_w, out)
 
+    def _check_jitter(self, jitter: torch.Tensor, n: int):
+        if jitter.dtype != torch.float32 or tuple(jitter.shape) != (n, _lib.JITTER_FLOATS):
+            raise RuntimeError(f"jitter must be fp32 [N,{_lib.JITTER_FLOATS}] (phdfx.jitter_params), got "
+                               f"{jitter.dtype} {tuple(jitter.shape)}")
+        self._check_dev(jitter, "jitter")
+
     @torch.no_grad()
     def preprocess_u8(self, frames: torch.Tensor, boxes: Optional[torch.Tensor] = None,
-                      flip_w: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """K1 alone: uint8 [N,H,W,3] -> bf16 NHWC4p [N,224,232,4] (the trunk's input layout)."""
+                      flip_w: bool = False, out: Optional[torch.Tensor] = None,
+                      jitter: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """K1 alone: uint8 [N,H,W,3] -> bf16 NHWC4p [N,224,232,4] (the trunk's input layout); jitter as extract_u8."""
         self._check_dev(frames, "frames")
         n, H, W, _ = frames.shape
         if out is None:
@@ -150,13 +175,20 @@ class B200Backbone:
             raise RuntimeError("out must be bf16 [N,224,232,4]")
         else:
             self._check_dev(out, "out")
+        if jitter is not None:
+            self._check_jitter(jitter, n)
         with torch.cuda.device(self.device):
             for i in range(0, n, self.max_frames):
                 m = min(self.max_frames, n - i)
                 bp = boxes[i:i + m].data_ptr() if boxes is not None else None
-                _lib.check(
-                    self._lib.phdfx_preprocess_u8(self._h, frames[i:i + m].data_ptr(), m, H, W, bp, int(flip_w),
-                                                  out[i:i + m].data_ptr(), self._stream()), self._h)
+                if jitter is None:
+                    rc = self._lib.phdfx_preprocess_u8(self._h, frames[i:i + m].data_ptr(), m, H, W, bp, int(flip_w),
+                                                       out[i:i + m].data_ptr(), self._stream())
+                else:
+                    rc = self._lib.phdfx_preprocess_u8_jitter(self._h, frames[i:i + m].data_ptr(), m, H, W, bp,
+                                                              int(flip_w), jitter[i:i + m].data_ptr(),
+                                                              out[i:i + m].data_ptr(), self._stream())
+                _lib.check(rc, self._h)
         return out
 
     @torch.no_grad()

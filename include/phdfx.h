@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PHDFX_VERSION 101 /* major*100 + minor */
+#define PHDFX_VERSION 102 /* major*100 + minor */
 
 typedef struct phdfx phdfx_t;
 
@@ -89,6 +89,16 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
 int phdfx_preprocess_u8(phdfx_t* h, const uint8_t* d_frames_hwc, int n, int H, int W, const int32_t* d_boxes,
                         int flip_w, void* d_out_nhwc4p, void* stream);
 
+/* K1 with the reference's colour-jitter augmentation in front of Normalize (src/dataset.py:188-198, the `cjitter`
+ * variant of --augment: torchvision v2 ColorJitter(brightness=0.3, contrast=0.3, saturation=0.2, hue=0.05) on the
+ * resized [0,1] clip, one parameter draw per clip).  d_jitter: device float [n][12], one row per FRAME (repeat a
+ * clip's draw for its frames): [0..3] the four ops in application order (0 brightness, 1 contrast, 2 saturation,
+ * 3 hue — ColorJitter.make_params' fn_idx), [4] brightness factor, [5] contrast factor, [6] (float)(1.0 - contrast),
+ * [7] saturation factor, [8] (float)(1.0 - saturation), [9] hue factor, [10..11] unused.  Two launches (the contrast
+ * op needs the frame's mean grey level first). */
+int phdfx_preprocess_u8_jitter(phdfx_t* h, const uint8_t* d_frames_hwc, int n, int H, int W, const int32_t* d_boxes,
+                               int flip_w, const float* d_jitter, void* d_out_nhwc4p, void* stream);
+
 /* Seam A repack: fp32 NCHW [n,3,224,224], already normalised (the tensor the reference feeds to backbone(), :295)
  * -> NHWC4p bf16 (NULL = arena input buffer). */
 int phdfx_nchw_f32_to_nhwc_bf16(phdfx_t* h, const float* d_x_nchw, int n, void* d_out_nhwc4p, void* stream);
@@ -107,6 +117,10 @@ int phdfx_forward_timed(phdfx_t* h, const void* d_in_nhwc4p, int n, float* d_fea
 /* Seam B: preprocess + trunk. */
 int phdfx_extract_u8(phdfx_t* h, const uint8_t* d_frames_hwc, int n, int H, int W, const int32_t* d_boxes,
                      int flip_w, float* d_feats, void* stream);
+
+/* Seam B with colour jitter (phdfx_preprocess_u8_jitter + trunk). */
+int phdfx_extract_u8_jitter(phdfx_t* h, const uint8_t* d_frames_hwc, int n, int H, int W, const int32_t* d_boxes,
+                            int flip_w, const float* d_jitter, float* d_feats, void* stream);
 
 /* Per-layer hook (parity tests, ncu, per-layer benchmark).  d_in / d_residual / d_out use the layer's own
  * layouts: NHWC bf16 activations (NHWC4p for the stem input); for a gap layer d_out is fp32 [n][cout]. */

@@ -101,6 +101,100 @@ def hflip(video: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(video[..., ::-1])
 
 
+# ---------------------------------------------------------------------------------------------------- colour jitter
+# /root/reference/src/dataset.py:188-198 `_aug_color_jitter`: T.ColorJitter(brightness=0.3, contrast=0.3,
+# saturation=0.2, hue=0.05) applied ONCE to the whole (T,3,224,224) clip in [0,1] (one parameter draw per clip),
+# before Normalize (:413-429).  torchvision 0.26.0 transforms/v2/_color.py:146-173 (make_params: fn_idx =
+# randperm(4), factors uniform; transform: the four ops in fn_idx order: 0 brightness, 1 contrast, 2 saturation,
+# 3 hue) and transforms/v2/functional/_color.py: _rgb_to_grayscale_image :31-48, _blend :92-97,
+# adjust_brightness_image :112-123, adjust_saturation_image :149-165, adjust_contrast_image :188-205,
+# _rgb_to_hsv :300-337, _hsv_to_rgb :340-367, adjust_hue_image :370-395.
+# Python-float factors reach the fp32 kernels as float32(factor); `alpha = 1.0 - ratio` is formed in double first.
+JITTER_BRIGHTNESS, JITTER_CONTRAST, JITTER_SATURATION, JITTER_HUE = 0, 1, 2, 3
+
+
+def _gray(x):
+    """_rgb_to_grayscale_image: r.mul(0.2989).add_(g, alpha=0.587).add_(b, alpha=0.114); ATen's add-with-alpha is
+    a fused multiply-add in its vectorised loop."""
+    f32 = np.float32
+    r, g, b = x[:, 0], x[:, 1], x[:, 2]
+    return _fma(b, f32(0.114), _fma(g, f32(0.587), _mul(r, f32(0.2989))))
+
+
+def _blend(x, other, ratio: float):
+    """_blend: image1.mul(ratio).add_(image2, alpha=1.0 - ratio).clamp_(0, 1)."""
+    f32 = np.float32
+    return np.clip(_fma(other, f32(1.0 - float(ratio)), _mul(x, f32(ratio))), f32(0), f32(1)).astype(np.float32)
+
+
+def _adjust_hue(x, hue: float):
+    f32 = np.float32
+    r, g, b = x[:, 0], x[:, 1], x[:, 2]
+    maxc = x.max(axis=1)
+    minc = x.min(axis=1)
+    eqc = maxc == minc
+    cr = (maxc - minc).astype(np.float32)
+    s = (cr / np.where(eqc, f32(1), maxc)).astype(np.float32)
+    div = np.where(eqc, f32(1), cr).astype(np.float32)
+    rc = ((maxc - r) / div).astype(np.float32)
+    gc = ((maxc - g) / div).astype(np.float32)
+    bc = ((maxc - b) / div).astype(np.float32)
+    neq_r = maxc != r
+    eq_g = maxc == g
+    hg = ((rc + f32(2.0)).astype(np.float32) - bc).astype(np.float32) * (eq_g & neq_r)
+    hr = (bc - gc).astype(np.float32) * (~neq_r)
+    hb = ((gc + f32(4.0)).astype(np.float32) - rc).astype(np.float32) * (neq_r & ~eq_g)
+    h = ((hr + hg).astype(np.float32) + hb).astype(np.float32)
+    h = np.fmod((h * f32(1.0 / 6.0)).astype(np.float32) + f32(1.0), f32(1.0)).astype(np.float32)
+    # h.add_(hue_factor).remainder_(1.0)
+    h = np.remainder((h + f32(hue)).astype(np.float32), f32(1.0)).astype(np.float32)
+    v = maxc
+    h6 = (h * f32(6)).astype(np.float32)
+    i = np.floor(h6)
+    f = (h6 - i).astype(np.float32)
+    i = np.remainder(i.astype(np.int32), 6)
+    sxf = (s * f).astype(np.float32)
+    oms = (f32(1.0) - s).astype(np.float32)
+    q = np.clip(((f32(1.0) - sxf).astype(np.float32) * v).astype(np.float32), 0, 1)
+    t = np.clip(((sxf + oms).astype(np.float32) * v).astype(np.float32), 0, 1)
+    pp = np.clip((oms * v).astype(np.float32), 0, 1)
+    vpqt = np.stack([v, pp, q, t], axis=0)  # (4, T, H, W)
+    select = np.array([[0, 2, 1, 1, 3, 0], [3, 0, 0, 2, 1, 1], [1, 1, 3, 0, 0, 2]])
+    out = np.stack([np.take_along_axis(vpqt, select[c][i][None], axis=0)[0] for c in range(3)], axis=1)
+    return out.astype(np.float32)
+
+
+def color_jitter(x01: np.ndarray, fn_idx, brightness: float, contrast: float, saturation: float, hue: float):
+    """x01: (T,3,H,W) fp32 in [0,1] -> jittered clip, torchvision v2 ColorJitter.transform with explicit params."""
+    f32 = np.float32
+    x = x01.astype(np.float32)
+    for fn in fn_idx:
+        fn = int(fn)
+        if fn == JITTER_BRIGHTNESS:  # image.mul(factor).clamp_(0, 1)
+            x = np.clip(_mul(x, f32(brightness)), f32(0), f32(1)).astype(np.float32)
+        elif fn == JITTER_CONTRAST:  # blend with the per-frame mean grey level
+            mean = _gray(x).reshape(x.shape[0], -1).mean(axis=1, dtype=np.float64).astype(np.float32)
+            x = _blend(x, mean[:, None, None, None], contrast)
+        elif fn == JITTER_SATURATION:
+            x = _blend(x, _gray(x)[:, None], saturation)
+        elif fn == JITTER_HUE:
+            x = _adjust_hue(x, hue)
+        else:
+            raise ValueError(fn)
+    return x
+
+
+def crop_resize_jitter_normalize(frames_u8: np.ndarray, box, fn_idx, brightness, contrast, saturation, hue,
+                                 flip: bool = False, aten_path: str = "worker") -> np.ndarray:
+    """dataset.py:141-152 -> [:166 hflip] -> :188-198 colour jitter -> :429 Normalize."""
+    u8 = crop_resize_u8(frames_u8, box, 224, aten_path)
+    x = u8.astype(np.float32) / np.float32(255.0)
+    if flip:
+        x = np.ascontiguousarray(x[..., ::-1])
+    x = color_jitter(x, fn_idx, brightness, contrast, saturation, hue)
+    return ((x - IMAGENET_MEAN[None, :, None, None]) / IMAGENET_STD[None, :, None, None]).astype(np.float32)
+
+
 def to_nhwc4p_bf16_bits(x_nchw_f32: np.ndarray) -> np.ndarray:
     """fp32 (N,3,224,224) -> uint16 bf16 bit patterns in the library's NHWC4p layout (N,224,232,4), RNE rounding."""
     n = x_nchw_f32.shape[0]

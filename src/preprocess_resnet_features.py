@@ -222,16 +222,32 @@ def main(argv=None):
         return backbone.extract_u8(fr, bx.to(device, non_blocking=True), flip_w=flip).view(Bv, Tt, -1)
 
     def jitter_variant(frames: torch.Tensor, boxes: torch.Tensor, clip_ids) -> torch.Tensor:
-        """Colour-jitter variant in synthetic mode: the reference's recipe (src/dataset.py:188-198: ColorJitter on
-        the resized [0,1] clip, then Normalize) evaluated on the device, one jitter draw per clip."""
+        """Colour-jitter variant in synthetic mode — the reference's recipe (src/dataset.py:188-198: ColorJitter on the
+        resized [0,1] clip, one draw per clip, then Normalize).  The draw comes from torchvision's own
+        ColorJitter.make_params under a per-clip seed; with --backend b200 the ops run inside K1
+        (phdfx_extract_u8_jitter), with --backend torch torchvision applies them."""
         import torch.nn.functional as F
         from torchvision.transforms import v2 as T2
 
         jit = T2.ColorJitter(brightness=0.3, contrast=0.3, saturation=0.2, hue=0.05)
+        Bv, Tt, H, W, _ = frames.shape
+        if args.backend == "b200":
+            import phdfx
+
+            rows = []
+            for b in range(Bv):
+                torch.manual_seed(args.jitter_seed * 1_000_003 + int(clip_ids[b]))
+                prm = jit.make_params([])
+                rows.append(phdfx.jitter_params(prm["fn_idx"], prm["brightness_factor"], prm["contrast_factor"],
+                                                prm["saturation_factor"], prm["hue_factor"]))
+            jrows = torch.stack(rows).repeat_interleave(Tt, dim=0).to(device, non_blocking=True)
+            fr = frames.view(Bv * Tt, H, W, 3).to(device, non_blocking=True)
+            bx = boxes.to(torch.int32).repeat_interleave(Tt, dim=0).to(device, non_blocking=True)
+            return backbone.extract_u8(fr, bx, jitter=jrows).view(Bv, Tt, -1)
         mean = torch.tensor(IMAGENET_MEAN, device=device).view(1, 3, 1, 1)
         std = torch.tensor(IMAGENET_STD, device=device).view(1, 3, 1, 1)
         outs = []
-        for b in range(frames.shape[0]):
+        for b in range(Bv):
             top, left, hh, ww = (int(v) for v in boxes[b])
             crop = frames[b, :, top:top + hh, left:left + ww].to(device).permute(0, 3, 1, 2).float()
             if (hh, ww) != (224, 224):

@@ -91,6 +91,55 @@ def test_preprocess_hflip(eng):
     assert np.array_equal(got.view(torch.int16).cpu().numpy().view(np.uint16), want)
 
 
+def _jitter_rows(cases, frames_per_case):
+    rows = [phdfx.jitter_params(*c) for c in cases for _ in range(frames_per_case)]
+    return torch.stack(rows).cuda()
+
+
+@pytest.mark.parametrize("H,W,box", [(224, 224, (0, 0, 224, 224)), (300, 280, (10, 20, 231, 231))])
+def test_preprocess_color_jitter_vs_oracle(eng, H, W, box):
+    """K1's colour-jitter variant (the reference's `cjitter`, src/dataset.py:188-198) against the oracle (pinned to
+    torchvision and to the reference's own function in tests/test_oracle_preprocess.py): two clips with different
+    draws in one call, several op orders, with and without the horizontal flip.  fp32 pipeline -> bf16: values agree
+    except where a last-ulp fp32 difference flips the bf16 rounding (<= 0.2 % of the values, by one bf16 step)."""
+    cases = [((0, 1, 2, 3), 1.21, 0.83, 1.13, 0.031), ((3, 1, 0, 2), 0.74, 1.27, 0.86, -0.044),
+             ((2, 3, 1, 0), 1.05, 0.95, 1.19, 0.05), ((1, 0, 3, 2), 0.9, 1.1, 0.8, -0.05)]
+    frames = R.seeded_frames(2 * len(cases), H, W, 51)
+    frames[0, :40] = frames[0, :40, :, :1]  # a grey band (max == min in the hue op)
+    boxes = torch.tensor([box] * frames.shape[0], dtype=torch.int32, device="cuda")
+    rows = _jitter_rows(cases, 2)
+    for flip in (False, True):
+        got = eng.preprocess_u8(torch.from_numpy(frames).cuda(), boxes, flip_w=flip, jitter=rows)
+        got_f = got.float().cpu().numpy()
+        for k, c in enumerate(cases):
+            want = P.crop_resize_jitter_normalize(frames[2 * k:2 * k + 2], box, *c, flip=flip)
+            want_bits = P.to_nhwc4p_bf16_bits(want)
+            want_f = (want_bits.astype(np.uint32) << 16).view(np.float32)
+            g = got_f[2 * k:2 * k + 2]
+            diff = np.abs(g - want_f)
+            assert (diff > 0).mean() <= 2e-3, (k, flip, (diff > 0).mean())
+            assert diff.max() <= 0.0157, (k, flip, diff.max())  # one bf16 step at |x| < 4
+            assert np.array_equal(g[:, :, :4], want_f[:, :, :4]) and np.array_equal(g[..., 3], want_f[..., 3])
+
+
+def test_extract_with_color_jitter_vs_c_oracle(eng, backbone):
+    """Seam B with the jitter variant end to end: features within the trunk's tolerance of the fp32 C oracle fed with
+    the oracle's jittered crops."""
+    frames = R.seeded_frames(2, 260, 250, 52)
+    box = (5, 7, 240, 240)
+    case = ((1, 3, 0, 2), 1.18, 0.77, 1.2, -0.02)
+    feats = eng.extract_u8(torch.from_numpy(frames).cuda(), torch.tensor([box] * 2, dtype=torch.int32, device="cuda"),
+                           jitter=_jitter_rows([case], 2))
+    assert eng.launches == 42  # two K1 launches (grey-level row sums, then the fused jitter + normalise) + the trunk
+    ref = R.features(P.crop_resize_jitter_normalize(frames, box, *case), R.param_list(backbone))
+    err, cos = frame_errors(feats.cpu().numpy(), ref)
+    assert err.max() <= NORM_TOL and cos.min() >= COS_TOL, (err, cos)
+    plain = eng.extract_u8(torch.from_numpy(frames).cuda(), torch.tensor([box] * 2, dtype=torch.int32, device="cuda"))
+    assert not torch.equal(plain, feats)
+    with pytest.raises(RuntimeError, match="jitter"):
+        eng.extract_u8(torch.from_numpy(frames).cuda(), None, jitter=torch.zeros(2, 10, device="cuda"))
+
+
 def test_preprocess_whole_frame_when_no_boxes(eng):
     frames = R.seeded_frames(2, 224, 224, 23)
     got = eng.preprocess_u8(torch.from_numpy(frames).cuda(), None)
