@@ -126,11 +126,16 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
   const int row_cap = (3 * W + 32 + 15) & ~15;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(s_rows);  // [3][256]
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
-    const int c = i >> 8;
-    const float x01 = __fdiv_rn(static_cast<float>(i & 255), 255.0f);             // frames.to(float32) / 255.0
-    lut[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]));    // Normalize, then bf16
+  __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(s_rows);  // [3][256] (KIND_PLAIN)
+  float* lut01 = reinterpret_cast<float*>(s_rows);                // [256] u8 / 255 (jitter kinds; same 1536 bytes)
+  if (KIND == KIND_PLAIN) {
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+      const int c = i >> 8;
+      const float x01 = __fdiv_rn(static_cast<float>(i & 255), 255.0f);             // frames.to(float32) / 255.0
+      lut[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]));    // Normalize, then bf16
+    }
+  } else {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut01[i] = __fdiv_rn(static_cast<float>(i), 255.0f);
   }
   __syncthreads();
   uint8_t* s0 = s_rows + kK1LutBytes + static_cast<size_t>(warp) * 2 * row_cap;
@@ -229,7 +234,7 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
           if (KIND == KIND_PLAIN)
             r[c] = reinterpret_cast<const uint16_t*>(lut)[c * 256 + u8];
           else
-            px[c] = __fdiv_rn(static_cast<float>(u8), 255.0f);  // frames.to(float32) / 255.0
+            px[c] = lut01[u8];  // frames.to(float32) / 255.0
         }
         if (KIND == KIND_JITTER_SUMS) {
           jit_apply(px, prm, 0.0f, true);

@@ -14,9 +14,11 @@
 //             a step's even/odd conv rows go to adjacent 64-column halves of one of two TMEM buffers
 //   warp 2    DMA: TMA store of pooled rows (56 px x 64 ch = 7 KB each); owns the TMEM allocation
 //   warp 4-11 epilogue, two warps per TMEM lane quadrant (32 channels each).  Thread q owns conv column q:
-//             vertical 3-max of rows 2i-1, 2i, 2i+1 in REGISTERS (row 2i-1 is carried from the previous step), the
-//             result goes to a swizzled smem row, then the horizontal 3-max (columns 2j-1..2j+1) + store staging.
-//             No ReLU instruction anywhere: the horizontal max starts at 0 and max(0, max(v)) == max-pool(relu(v)).
+//             vertical 3-max of rows 2i-1, 2i, 2i+1 in REGISTERS (row 2i-1 is carried from the previous step), then the
+//             horizontal 3-max (columns 2j-1..2j+1) by warp shuffles — the neighbours of a centre column are one lane
+//             away; only lane 0's left neighbour crosses a warp (64 B exchange slot) — and the pooled row goes straight
+//             to the store staging.  The conv rows never touch shared memory, which the N=64 MMAs' operand reads
+//             keep busy.  No ReLU instruction anywhere: the max starts at 0 and max(0, max(v)) == max-pool(relu(v)).
 #pragma once
 #include "ptx_sm100.cuh"
 
@@ -39,13 +41,13 @@ struct StemPoolSmem {
   static constexpr int RING = 0;                                           // 8 x 4096
   static constexpr int ZERO = RING + kSpPairSlots * 2 * kSpRowPitch;       // 2048 + 256 zero bytes
   static constexpr int WEIGHTS = ZERO + kSpRowPitch + 1024;                // 1024-aligned
-  static constexpr int CONV = WEIGHTS + kSpWeightBytes;                    // 2 x 14336 vertical-max rows, 1024-aligned
-  static constexpr int POOL = CONV + 2 * kSpConvRowBytes;                  // 2 x 8192
+  static constexpr int POOL = WEIGHTS + kSpWeightBytes;                    // 2 x 8192, 1024-aligned
   static constexpr int BIAS = POOL + 2 * kSpPoolRowBytes;                  // 64 floats
   static constexpr int BARS = BIAS + 256;
-  static constexpr int TOTAL = BARS + 512;
+  static constexpr int XCHG = BARS + 512;                                  // [2 parities][2 halves][4 quadrants][64 B]
+  static constexpr int TOTAL = XCHG + 1024;
 };
-static_assert(StemPoolSmem::WEIGHTS % 1024 == 0 && StemPoolSmem::CONV % 1024 == 0 && StemPoolSmem::POOL % 1024 == 0,
+static_assert(StemPoolSmem::WEIGHTS % 1024 == 0 && StemPoolSmem::POOL % 1024 == 0,
               "swizzled regions must be 1024-byte aligned");
 
 struct StemPoolParams {
@@ -241,7 +243,6 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;  // 32-channel half of the 64 output channels
     const int q = quad * 32 + lane;    // conv output column owned by this thread (TMEM lane)
-    const int et = threadIdx.x - 128;  // 0..255
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + half * 32;
     const float4* sb4 = reinterpret_cast<const float4*>(s_bias + half * 32);
     int buf = 0;
@@ -295,44 +296,42 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
           ev[j] = m;
         }
         have_carry = true;
-        uint8_t* vrow = smem + L::CONV + (k & 1) * kSpConvRowBytes;
-        if (q < kSpOut) {
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            uint4 o;
-            o.x = *reinterpret_cast<uint32_t*>(&ev[4 * c4 + 0]);
-            o.y = *reinterpret_cast<uint32_t*>(&ev[4 * c4 + 1]);
-            o.z = *reinterpret_cast<uint32_t*>(&ev[4 * c4 + 2]);
-            o.w = *reinterpret_cast<uint32_t*>(&ev[4 * c4 + 3]);
-            *reinterpret_cast<uint4*>(vrow + q * 128 + (((half * 4 + c4) ^ (q & 7)) << 4)) = o;
-          }
-        }
-        named_barrier_sync(1, kSpEpiThreads);  // the vertical-max row is complete
         // horizontal 3-max (columns 2j-1 .. 2j+1, >= 0) starting from 0: the 0 is both the ReLU and the -inf padding
-        // of the reference's MaxPool2d (its input is post-ReLU, resnet.py:270-271)
+        // of the reference's MaxPool2d (its input is post-ReLU, resnet.py:270-271).  Thread q holds column q, so the
+        // neighbours of an even (= centre) column are one lane away: two warp shuffles per register.  Only lane 0's left
+        // neighbour lives in another warp (lane 31 of the previous lane quadrant, same channel half): those 64 bytes
+        // go through a tiny double-buffered exchange slot.  Nothing else of the conv row touches shared memory.
+        uint32_t* xch = reinterpret_cast<uint32_t*>(smem + L::XCHG) + ((k & 1) * 8 + half * 4 + quad) * 16;
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xch[j] = *reinterpret_cast<uint32_t*>(&ev[j]);
+        }
+        named_barrier_sync(1, kSpEpiThreads);
+        const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+        __nv_bfloat162 m[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t self = *reinterpret_cast<uint32_t*>(&ev[j]);
+          uint32_t lft = __shfl_up_sync(0xffffffffu, self, 1);
+          const uint32_t rgt = __shfl_down_sync(0xffffffffu, self, 1);
+          if (lane == 0) lft = quad > 0 ? (xch - 16)[j] : 0u;  // column q-1 of the previous quadrant; none left of q = 0
+          m[j] = __hmax2(__hmax2(z, ev[j]), __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&lft),
+                                                    *reinterpret_cast<const __nv_bfloat162*>(&rgt)));
+        }
         const int pbuf = k & 1;
         if (k >= 2) mbar_wait(&pool_free[pbuf], ((k >> 1) - 1) & 1);
         uint8_t* pool_row = smem + L::POOL + pbuf * kSpPoolRowBytes;
-        for (int task = et; task < kSpPool * 8; task += kSpEpiThreads) {
-          const int j = task >> 3;
-          const int c = task & 7;
-          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
-          __nv_bfloat162 m[4] = {z, z, z, z};
+        if (!(q & 1) && q < kSpOut) {  // even columns are the pooling centres: pooled column j = q / 2
+          const int j = q >> 1;
 #pragma unroll
-          for (int dc = 0; dc < 3; ++dc) {
-            const int col = 2 * j - 1 + dc;
-            if (col < 0) continue;
-            const uint4 val = *reinterpret_cast<const uint4*>(vrow + col * 128 + ((c ^ (col & 7)) << 4));
-            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&val);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) m[t] = __hmax2(m[t], pv[t]);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&m[4 * c4 + 0]);
+            o.y = *reinterpret_cast<uint32_t*>(&m[4 * c4 + 1]);
+            o.z = *reinterpret_cast<uint32_t*>(&m[4 * c4 + 2]);
+            o.w = *reinterpret_cast<uint32_t*>(&m[4 * c4 + 3]);
+            *reinterpret_cast<uint4*>(pool_row + j * 128 + (((half * 4 + c4) ^ (j & 7)) << 4)) = o;
           }
-          uint4 o;
-          o.x = *reinterpret_cast<uint32_t*>(&m[0]);
-          o.y = *reinterpret_cast<uint32_t*>(&m[1]);
-          o.z = *reinterpret_cast<uint32_t*>(&m[2]);
-          o.w = *reinterpret_cast<uint32_t*>(&m[3]);
-          *reinterpret_cast<uint4*>(pool_row + j * 128 + ((c ^ (j & 7)) << 4)) = o;
         }
         fence_proxy_async_smem();
         __syncwarp();
