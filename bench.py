@@ -313,15 +313,20 @@ def run_b200(args):
     k1j_bytes = BATCH * (2 * IMG * IMG * 3 + IMG * 232 * 4 * 2)
 
     # ---- end to end through the host-buffer API ----------------------------------------------------------------
-    host = torch.empty(n_batches * BATCH, IMG, IMG, 3, dtype=torch.uint8).pin_memory()
-    host.copy_(seq[:n_batches * BATCH].cpu())
+    # the host-side sequence: K batches (at most 32 = 1.2 GB pinned) taken cyclically from the same frames, so ONE call
+    # streams the whole timed region (upload of batch i+1 / download of batch i-1 overlap the trunk of batch i, and
+    # the pipeline fills and drains once, as it does for a real sequence)
+    nb_e2e = max(2, min(K, 32))
+    host = torch.empty(nb_e2e * BATCH, IMG, IMG, 3, dtype=torch.uint8).pin_memory()
+    for b in range(nb_e2e):
+        host[b * BATCH:(b + 1) * BATCH].copy_(seq[(b % n_batches) * BATCH:(b % n_batches + 1) * BATCH])
+    torch.cuda.synchronize(dev)
     se = phdfx.StreamingExtractor(eng, batch=BATCH)
-    warm_out = torch.empty(BATCH, 2048, dtype=torch.float32).pin_memory()
-    se(host[:BATCH], None, out=warm_out)  # warm-up (allocates staging)
+    warm_out = torch.empty(2 * BATCH, 2048, dtype=torch.float32).pin_memory()
+    se(host[:2 * BATCH], None, out=warm_out)  # warm-up: allocates staging, captures the graph of both slots
     barrier()
-    # a single call over K batches: upload of batch i+1 / download of batch i-1 overlap the trunk of batch i
-    frames_k = host if K >= n_batches else host[:K * BATCH]
-    reps_e2e = max(1, (K * BATCH) // frames_k.shape[0])
+    frames_k = host
+    reps_e2e = max(1, (K + nb_e2e - 1) // nb_e2e)
     out_k = torch.empty(frames_k.shape[0], 2048, dtype=torch.float32).pin_memory()
     t0 = time.perf_counter()
     h2d = d2h = 0
