@@ -402,6 +402,27 @@ def test_chunking_over_max_frames(eng):
     assert not torch.isnan(feats).any() and feats.min() >= 0  # post-ReLU mean
 
 
+def test_empty_batch(eng):
+    """Zero frames in, zero rows out (no launch), on both seams."""
+    out = eng.extract_u8(torch.empty(0, 224, 224, 3, dtype=torch.uint8, device="cuda"), None)
+    assert tuple(out.shape) == (0, 2048) and eng.launches == 0
+    out = eng(torch.empty(0, 3, 224, 224, device="cuda"))
+    assert tuple(out.shape) == (0, 2048, 1, 1)
+
+
+def test_forward_timed_hook(eng):
+    """phdfx_forward_timed (in-situ per-launch timing, BASELINE config 3): same features as the plain call, one
+    positive time per launch, fused chains reported as one entry."""
+    frames = torch.from_numpy(R.seeded_frames(6, 224, 224, 15)).cuda()
+    x4 = eng.preprocess_u8(frames, None)
+    feats, times = eng.forward_timed(x4)
+    assert torch.equal(feats, eng.forward_nhwc4p(x4))
+    assert len(times) == 40 and all(ms > 0 for _, ms in times)
+    names = [nm for nm, _ in times]
+    assert names[0] == "conv1+maxpool" and "layer1.1.conv2+layer1.1.conv3+layer1.2.conv1" in names
+    assert "layer2.1.conv2+layer2.1.conv3" in names and names[-1] == "layer4.2.conv3"
+
+
 def test_deterministic(eng):
     frames = torch.from_numpy(R.seeded_frames(9, 224, 224, 10)).cuda()
     a = eng.extract_u8(frames, None).clone()
