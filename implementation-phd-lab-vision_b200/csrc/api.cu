@@ -369,8 +369,9 @@ int launch_conv_cg2_t(phdfx_t* h, const LayerMaps& maps, const ConvParams& p, cu
   return 0;
 }
 
-int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bool has_res, void* out, int n,
-                cudaStream_t st, int rev = 0) {
+int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, const void* res, void* out, int n,
+                cudaStream_t st, int rev = 0, long long* trace = nullptr) {
+  const bool has_res = res != nullptr;
   const Geo g = geometry(L);
   ConvParams p{};
   p.Cout = L.cout;
@@ -392,6 +393,7 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, bo
   p.kb_split = L.in2_buf >= 0 ? L.cin / 64 : g.num_kb;
   p.src2_stride = L.in2_buf >= 0 ? L.stride2 : 1;
   p.rev = rev;
+  p.trace = trace;
   if (g.mode == MODE_HALO)
     p.m_tiles = n * (g.P / g.halo_rt);
   else if (g.mode == MODE_STEM)
@@ -864,9 +866,9 @@ static int forward_impl(phdfx_t* h, const void* d_in, int n, float* d_feats, cud
       LayerMaps tmp;
       if (int rc = build_maps(h, L, d_in, nullptr, res, L.gap ? nullptr : out, n, &tmp)) return rc;
       tmp.o = h->maps[i].o;
-      if (int rc = launch_conv(h, L, tmp, res != nullptr, out, n, st, rev)) return rc;
+      if (int rc = launch_conv(h, L, tmp, res, out, n, st, rev)) return rc;
     } else {
-      if (int rc = launch_conv(h, L, h->maps[i], res != nullptr, out, n, st, rev)) return rc;
+      if (int rc = launch_conv(h, L, h->maps[i], res, out, n, st, rev)) return rc;
     }
     if (L.gap) wrote_feats = true;
   }
@@ -938,7 +940,27 @@ int phdfx_run_layer2(phdfx_t* h, int layer_id, const void* d_in, const void* d_i
   const void* res = L.res_buf >= 0 ? d_residual : nullptr;
   if (int rc = build_maps(h, L, d_in, L.in2_buf >= 0 ? d_in2 : nullptr, res, L.gap ? nullptr : d_out, n, &tmp))
     return rc;
-  return launch_conv(h, L, tmp, res != nullptr, d_out, n, st);
+  if (const char* path = getenv("PHDFX_CONV_TRACE")) {
+    // debug: clock64 timeline of CTA 0 of a conv_igemm_kernel launch (1-CTA kernel only; synchronises)
+    long long* d_trace = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_trace, 32 * 32 * sizeof(long long)));
+    CUDA_TRY(h, cudaMemset(d_trace, 0, 32 * 32 * sizeof(long long)));
+    int rc = launch_conv(h, L, tmp, res, d_out, n, st, 0, d_trace);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    std::vector<long long> host(32 * 32);
+    CUDA_TRY(h, cudaMemcpy(host.data(), d_trace, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_trace);
+    if (FILE* f = fopen(path, "w")) {
+      for (int k = 0; k < 32; ++k) {
+        fprintf(f, "%d", k);
+        for (int e = 0; e < 32; ++e) fprintf(f, " %lld", host[k * 32 + e]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    return rc;
+  }
+  return launch_conv(h, L, tmp, res, d_out, n, st);
 }
 
 int phdfx_run_layer(phdfx_t* h, int layer_id, const void* d_in, const void* d_residual, void* d_out, int n,

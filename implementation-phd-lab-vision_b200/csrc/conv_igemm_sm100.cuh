@@ -58,6 +58,7 @@ struct ConvParams {
                    // on the rows its predecessor wrote last — the part of the activation tensor still resident in L2
   const float* bias;  // [Cout] folded BN bias
   float* feats;       // MODE_GAP: [n_frames, Cout]
+  long long* trace;   // debug (PHDFX_CONV_TRACE): CTA 0 writes clock64() of pipeline events, [tile < 32][32 events]
 };
 
 constexpr int kBlockM = 128;
@@ -133,6 +134,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
+  // debug timeline: event e of this CTA's k-th tile (CTA 0 only, first 32 tiles)
+  auto mark = [&](int k, int e) {
+    if (p.trace != nullptr && blockIdx.x == 0 && k < 32 && lane == 0) p.trace[k * 32 + e] = clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -220,6 +225,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           ch = (m_blk - cn * tpf) * p.halo_rt - 1;  // first input row of the patch (-1 = zero halo)
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (kb == 0) mark((lt - blockIdx.x) / gridDim.x, 0);
           if (MODE == MODE_HALO) {
             // kb = cb * 9 + tap: one input patch per 64-channel block, then its nine weight tiles
             const int cb = kb / 9;
@@ -275,6 +281,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             stage = 0;
             phase ^= 1;
           }
+          if (kb == p.num_kb - 1) mark((lt - blockIdx.x) / gridDim.x, 1);
         }
       }
     }
@@ -288,8 +295,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       uint32_t acc_phase = 0;
       int hseq = 0;  // MODE_HALO: patches consumed so far
       bool res_b_ready = false;  // RES_B: the nine resident weight tiles have landed (checked during the first tile)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tk = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tk) {
+        mark(tk, 2);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mark(tk, 3);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         // `ready`: the barrier of the stage about to be consumed is already known to be complete (probed while the
@@ -344,6 +354,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           }
         }
         res_b_ready = true;
+        mark(tk, 4);
         umma_commit_elect(&tmem_full[acc]);  // accumulator complete
         if (++acc == 2) {
           acc = 0;
@@ -373,6 +384,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const int row0 = m_blk * ((MODE == MODE_GAP) ? kGapRows : kBlockM);
             mbar_arrive_expect_tx(&res_full[b], kStageOutBytes);
             tma_load_2d(&mapR, &res_full[b], stage_out + b * kStageOutBytes, n_blk * BN + g * kGroupCols, row0);
+            if (g < 4) mark(t / GROUPS, 8 + g);
           } else {
             mbar_arrive(&res_full[b]);
           }
@@ -403,6 +415,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               tma_store_2d(&mapO, src, n_blk * BN + g * kGroupCols, m_blk * kBlockM);
             }
             tma_store_commit();
+            if (g < 4) mark(u / GROUPS, 12 + g);
           }
         }
       }
@@ -439,7 +452,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         srow = i * p.Q + j;
       }
 
+      if (warp == 4) mark(it, 16);
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (warp == 4) mark(it, 17);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 
@@ -447,6 +462,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int g = 0; g < GROUPS; ++g, ++jg) {
         const int b = jg % NB;
         mbar_wait(&res_full[b], (jg / NB) & 1);
+        if (warp == 4 && g < 4) mark(it, 18 + g);
         uint8_t* row_ptr = stage_out + b * kStageOutBytes + srow * 128;
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + g * kGroupCols + half * 32, v);
@@ -524,6 +540,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (MODE != MODE_GAP) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&out_full[b]);
+        if (warp == 4 && g < 4) mark(it, 22 + g);
       }
       // release the accumulator buffer to the MMA warp
       tc_fence_before();
