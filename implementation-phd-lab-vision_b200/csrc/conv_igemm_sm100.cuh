@@ -84,11 +84,15 @@ struct ConvCfg {
   static constexpr int HB = (MODE == MODE_HALO) ? (BN == 64 ? 3 : 4) : 0;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int A_TX = ((MODE == MODE_GAP) ? kGapRows : kBlockM) * ROWB;
-  static constexpr int NB = (MODE == MODE_GAP || MODE == MODE_HALO) ? 2 : 4;  // epilogue staging buffers
-  static constexpr int LOOK = (NB == 2) ? 1 : 2;               // residual loads run LOOK groups ahead of the stores
+  // BN = 256 1x1 convs (the expand convs with their residual): a residual TMA load takes ~2 800 cycles from issue to
+  // arrival while a group is processed in ~800 (PHDFX_CONV_TRACE), so three loads have to be in flight: 5 staging
+  // buffers, paid for with a single-buffered bias (one more named barrier per tile)
+  static constexpr bool DEEP = (BN == 256 && MODE == MODE_TILED);
+  static constexpr int NB = DEEP ? 5 : (MODE == MODE_GAP || MODE == MODE_HALO) ? 2 : 4;  // epilogue staging buffers
+  static constexpr int LOOK = DEEP ? 3 : (NB == 2) ? 1 : 2;    // residual loads run LOOK groups ahead of the stores
   static constexpr int GROUPS = BN / kGroupCols;
   static constexpr int SCRATCH_BYTES = (MODE == MODE_GAP) ? 2 * kBlockM * 33 * 4 : 0;
-  static constexpr int TAIL_BYTES = 1024 + 2 * BN * 4 + SCRATCH_BYTES;  // barriers + bias double buffer + scratch
+  static constexpr int TAIL_BYTES = 1024 + (DEEP ? 1 : 2) * BN * 4 + SCRATCH_BYTES;  // barriers + bias buffer(s) + scratch
   static constexpr int SMEM_MAX = 232448;                              // 227 KB
   static constexpr int NSTAGE_RAW =
       (SMEM_MAX - 1024 - TAIL_BYTES - NB * kStageOutBytes - HB * HALO_BYTES) / STAGE_BYTES;
@@ -436,7 +440,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int m_blk = tile / p.n_tiles;
       const int n_blk = tile - m_blk * p.n_tiles;
       const int n_base = n_blk * BN;
-      float* sb = s_bias + (it & 1) * BN;
+      float* sb = s_bias + (Cfg::DEEP ? 0 : (it & 1) * BN);
+      if (Cfg::DEEP && it > 0) named_barrier_sync(2, kEpiThreads);  // everyone is done with the previous tile's bias
       for (int i = et; i < BN; i += kEpiThreads) sb[i] = __ldg(&p.bias[n_base + i]);
       named_barrier_sync(1, kEpiThreads);
 
