@@ -277,7 +277,13 @@ def run_b200(args):
     achieved_tf = BATCH * FLOP_PER_FRAME / (trunk_ms / 1e3) / 1e12
     # DRAM traffic of the trunk's launches, from the committed `ncu --set full` capture of one step (not measured live)
     traffic = None
-    for cand in sorted((ROOT / "profiles").glob("r*/trunk_traffic_*.json")):
+    def _ver(pth):  # profiles/rNN/trunk_traffic_vMM.json -> (NN, MM): the newest capture wins
+        import re
+
+        m = re.search(r"r(\d+)[/\\]trunk_traffic_v(\d+)", str(pth))
+        return (int(m.group(1)), int(m.group(2))) if m else (0, 0)
+
+    for cand in sorted((ROOT / "profiles").glob("r*/trunk_traffic_*.json"), key=_ver):
         try:
             traffic = json.loads(cand.read_text())
             traffic["file"] = str(cand.relative_to(ROOT))
