@@ -677,9 +677,9 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
       return fail(h, PHDFX_ERR_INVALID, "layer %d: out_buf aliases in_buf or res_buf", i);
     if (L.kind != PHDFX_MAXPOOL) {
       const Geo g = (L.kind == PHDFX_STEM_POOL) ? Geo{} : geometry(L);
-      const int64_t wsz = (L.kind == PHDFX_STEM || L.kind == PHDFX_STEM_POOL)
-                              ? 7 * 64 * 32
-                              : static_cast<int64_t>(g.K) * L.cout;
+      const int64_t wsz = L.kind == PHDFX_STEM_POOL ? kSpWeightBytes / 2
+                          : L.kind == PHDFX_STEM    ? 7 * 64 * 32
+                                                    : static_cast<int64_t>(g.K) * L.cout;
       if (L.w_off < 0 || L.w_off + wsz > n_weights || L.b_off < 0 || L.b_off + L.cout > n_bias)
         return fail(h, PHDFX_ERR_INVALID, "layer %d: weight/bias offsets out of range", i);
       if (L.w_off % 8) return fail(h, PHDFX_ERR_INVALID, "layer %d: w_off must be a multiple of 8 elements", i);

@@ -10,8 +10,9 @@
 // K-chunk stride LBO = 16 B, 8-row-group stride SBO = 128 B) — the tensor core does the sliding window.  Rows outside
 // the image read a zeroed slot.  K = 7 filter rows x 32 (8 px x 4 ch; tap -1 and channel 3 carry zero weights).
 //   warp 0    producer: cp.async.bulk of input row PAIRS into a 16-slot ring (2 x 1856 B per slot)
-//   warp 1    MMA issuer: 14 tcgen05.mma (M=128, N=64, K=16) per conv row, weights resident in smem (28 KB);
-//             a step's even/odd conv rows go to adjacent 64-column halves of one of two TMEM buffers
+//   warp 1    MMA issuer: a step's even/odd conv rows go to adjacent 64-column halves of one of two TMEM buffers; an input
+//             row that feeds both (filter row e of the even, e-2 of the odd conv row) is ONE N=128 tcgen05.mma pair against
+//             the stacked filter rows: 8 N=64 + 10 N=128 MMAs (M=128, K=16) per step; weights resident in smem (68 KB)
 //   warp 2    DMA: TMA store of pooled rows (56 px x 64 ch = 7 KB each); owns the TMEM allocation
 //   warp 4-11 epilogue, two warps per TMEM lane quadrant (32 channels each).  Thread q owns conv column q:
 //             vertical 3-max of rows 2i-1, 2i, 2i+1 in REGISTERS (row 2i-1 is carried from the previous step), then the
@@ -32,7 +33,10 @@ constexpr int kSpBand = 16;                     // conv rows per work item
 constexpr int kSpBandsPerFrame = kSpOut / kSpBand;  // 7
 constexpr int kSpConvRowBytes = kSpOut * 128;   // 14336: one conv row, 112 px x 64 ch bf16
 constexpr int kSpPoolRowBytes = 8192;           // staging pitch (56 x 128 B = 7168 used)
-constexpr int kSpWeightBytes = 7 * 4096;        // [7][4 k-chunks][64 cout][8] bf16
+// weights: [7 filter rows][4 k-chunks][64 cout][8] bf16, then for e = 2..6 the STACKED pairs
+// [4 k-chunks][128 rows = filter row e (even conv row) | filter row e-2 (odd conv row)][8] (see the MMA warp)
+constexpr int kSpWeightBase = 7 * 4096;
+constexpr int kSpWeightBytes = kSpWeightBase + 5 * 8192;
 constexpr int kSpThreads = 384;
 constexpr int kSpEpiThreads = 256;
 constexpr int kSpEpiWarps = 8;
@@ -163,6 +167,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
     // ------------------------------------------------------------------ MMA issuer (whole warp, uniform flow)
     {
       constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+      constexpr uint32_t idesc128 = make_idesc_bf16(128, 128);
       const uint32_t ring_addr = smem_u32(smem + L::RING);
       const uint32_t zero_addr = smem_u32(smem + L::ZERO);
       const uint32_t w_addr = smem_u32(smem + L::WEIGHTS);
@@ -173,48 +178,70 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
       for (int b = blockIdx.x; b < num_bands; b += gridDim.x) {
         const Band band(b);
         int waited = band.j_first;  // first pair of this band not yet known to have landed
-        for (int pr = band.p_first; pr <= band.p_last; ++pr) {
+        // input row h of this band in the ring (or the zero slot outside the image)
+        auto a_of = [&](int h) -> uint32_t {
+          if (h < 0 || h >= kSpIn) return zero_addr;
+          const int seq = seq_base + ((h >> 1) - band.j_first);
+          return ring_addr + (seq % kSpPairSlots) * 2 * kSpRowPitch + (h & 1) * kSpRowPitch;
+        };
+        // two K = 16 MMAs of one input row: N = 64 against filter row `fr` into d, or N = 128 against the stacked pair
+        // `pair` (filter rows pair+2 | pair) into the whole 128-column step accumulator
+        auto mma_row = [&](uint32_t d, uint32_t a_row, int fr, int pair, bool first) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t adesc = make_nosw_desc(a_row + k * 32, 16, 128);
+            if (pair < 0)
+              umma_bf16_elect(d, adesc, make_nosw_desc(w_addr + fr * 4096 + k * 2048, 1024, 128), idesc,
+                              (first && k == 0) ? 0u : 1u);
+            else
+              umma_bf16_elect(d, adesc, make_nosw_desc(w_addr + kSpWeightBase + pair * 8192 + k * 4096, 2048, 128),
+                              idesc128, 1u);
+          }
+        };
+        for (int pr = band.p_first; pr <= band.p_last;) {
           // a step = (even row, odd row); the band's halo row (odd) is a step of its own
-          if (!(pr & 1) || pr == band.p_first) mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
-          // input row pairs pr-2 .. pr+1 feed this conv row; earlier ones were already waited for
-          const int need = pr + 1 > band.j_last ? band.j_last : pr + 1;
+          const bool both = !(pr & 1);
+          const int last = both ? pr + 1 : pr;
+          mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
+          // input row pairs pr-2 .. last+1 feed this step; earlier ones were already waited for
+          const int need = last + 1 > band.j_last ? band.j_last : last + 1;
           for (; waited <= need; ++waited) {
             const int seq = seq_base + (waited - band.j_first);
             mbar_wait(&pair_full[seq % kSpPairSlots], (seq / kSpPairSlots) & 1);
           }
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * 128 + (pr & 1) * 64;
-#pragma unroll
-          for (int r = 0; r < 7; ++r) {
-            const int h = 2 * pr + r - 3;
-            uint32_t a_row = zero_addr;
-            if (h >= 0 && h < kSpIn) {
-              const int seq = seq_base + ((h >> 1) - band.j_first);
-              a_row = ring_addr + (seq % kSpPairSlots) * 2 * kSpRowPitch + (h & 1) * kSpRowPitch;
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint64_t adesc = make_nosw_desc(a_row + k * 32, 16, 128);
-              const uint64_t bdesc = make_nosw_desc(w_addr + r * 4096 + k * 2048, 1024, 128);
-              umma_bf16_elect(d_tmem, adesc, bdesc, idesc, (r | k) != 0 ? 1u : 0u);
-            }
+          const uint32_t d_even = tmem_base + buf * 128, d_odd = d_even + 64;
+          if (!both) {
+            for (int r = 0; r < 7; ++r) mma_row(d_odd, a_of(2 * pr + r - 3), r, -1, r == 0);
+          } else {
+            // Input row h = 2*pr - 3 + e (e = 0..8) is filter row e of the even conv row AND filter row e-2 of the odd
+            // one.  Rows that feed only one of them go first (N = 64, initialising that half of the accumulator); the
+            // five rows that feed both are ONE N = 128 MMA pair each against the stacked filter rows [e | e-2] — 18
+            // instead of 28 MMAs per step, and the slow part of an MMA here is fetching A (overlapping 16-byte rows).
+            const int h0 = 2 * pr - 3;
+            mma_row(d_odd, a_of(h0 + 7), 5, -1, true);
+            mma_row(d_odd, a_of(h0 + 8), 6, -1, false);
+            mma_row(d_even, a_of(h0 + 0), 0, -1, true);
+            mma_row(d_even, a_of(h0 + 1), 1, -1, false);
+            for (int e = 2; e < 7; ++e) mma_row(d_even, a_of(h0 + e), 0, e - 2, false);
           }
-          if (pr & 1) {
-            umma_commit_elect(&tmem_full[buf]);
-            buf ^= 1;
-            if (buf == 0) buf_phase ^= 1;
-          }
-          // pair pr-2 is not needed by later rows
-          if (pr - 2 >= band.j_first) {
-            const int seq = seq_base + (pr - 2 - band.j_first);
-            umma_commit_elect(&pair_empty[seq % kSpPairSlots]);
-          }
-          if (pr == band.p_last) {
-            for (int j = (pr - 1 < band.j_first ? band.j_first : pr - 1); j <= band.j_last; ++j) {
+          umma_commit_elect(&tmem_full[buf]);
+          buf ^= 1;
+          if (buf == 0) buf_phase ^= 1;
+          // pairs below last-1 are not needed by later rows
+          for (int j = pr - 2; j <= last - 2; ++j) {
+            if (j >= band.j_first) {
               const int seq = seq_base + (j - band.j_first);
               umma_commit_elect(&pair_empty[seq % kSpPairSlots]);
             }
           }
+          if (last == band.p_last) {
+            for (int j = (last - 1 < band.j_first ? band.j_first : last - 1); j <= band.j_last; ++j) {
+              const int seq = seq_base + (j - band.j_first);
+              umma_commit_elect(&pair_empty[seq % kSpPairSlots]);
+            }
+          }
+          pr = last + 1;
         }
         seq_base += band.pairs();
       }

@@ -59,14 +59,18 @@ def pack_stem(w: torch.Tensor) -> torch.Tensor:
 
 
 def pack_stem_pool(w: torch.Tensor) -> torch.Tensor:
-    """[64, 3, 7, 7] fp32 -> flat bf16 [7 (filter row)][4 (k-chunk)][64 (cout)][8]: the shared-memory image of the
-    fused stem kernel's B operand (K-major, no swizzle: 8x16 B core matrices, k-chunk stride 1024 B);
-    k = chunk*8 + e = (s+1)*4 + c."""
+    """[64, 3, 7, 7] fp32 -> flat bf16: the shared-memory image of the fused stem kernel's B operands (K-major, no swizzle:
+    8x16 B core matrices), k = chunk*8 + e = (s+1)*4 + c:
+      [7 (filter row)][4 (k-chunk)][64 (cout)][8]                      one filter row, N = 64
+      [5 (e = 2..6)][4 (k-chunk)][128 = filter row e | filter row e-2][8]  stacked pairs, N = 128: an input row that is
+          filter row e of an even conv row is filter row e-2 of the next (odd) one (stem_pool_sm100.cuh, MMA warp)."""
     cout, cin, r, s = w.shape
     assert (cout, cin, r, s) == (64, 3, 7, 7), w.shape
     out = torch.zeros(7, 64, 8, 4, dtype=torch.float32)
     out[:, :, 1:8, 0:3] = w.permute(2, 0, 3, 1)
-    return out.reshape(7, 64, 4, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16).reshape(-1)
+    rows = out.reshape(7, 64, 4, 8).permute(0, 2, 1, 3).contiguous()  # [7][4][64][8]
+    pairs = torch.cat([rows[2:7], rows[0:5]], dim=2)  # [5][4][128][8]: rows 0..63 = filter row e, 64..127 = e-2
+    return torch.cat([rows.reshape(-1), pairs.contiguous().reshape(-1)]).to(torch.bfloat16)
 
 
 def _children(backbone: nn.Module):

@@ -39,7 +39,8 @@ typedef enum phdfx_layer_kind {
   PHDFX_STEM = 1,    /* 7x7 stride-2 pad-3 conv, 3 -> 64 channels, on the NHWC4p input layout */
   PHDFX_MAXPOOL = 2, /* 3x3 stride-2 pad-1 max-pool */
   PHDFX_STEM_POOL = 3, /* stem conv + ReLU + 3x3/2 max-pool fused: NHWC4p in, [n][56][56][64] out; weights in the
-                          no-swizzle smem image layout [7][4][64][8] (phdfx/weights.py: pack_stem_pool) */
+                          no-swizzle smem image layout [7][4][64][8] + stacked row pairs [5][4][128][8]
+                          (phdfx/weights.py: pack_stem_pool) */
 } phdfx_layer_kind;
 
 /* One entry of the execution list handed to phdfx_load_weights.  Mirrors one conv(+folded BN)(+ReLU)(+residual)

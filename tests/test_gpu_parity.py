@@ -302,15 +302,17 @@ def test_chains_are_bit_identical_to_per_conv_kernels(backbone):
 
 @pytest.mark.parametrize("n", [1, 3])
 def test_unfused_stem_and_maxpool_kernels(backbone, n):
-    """The separate implicit-GEMM stem and max-pool kernels (fuse_stem_pool=False) and the fused kernel agree
-    bit-for-bit on the whole path."""
+    """The separate implicit-GEMM stem and max-pool kernels (fuse_stem_pool=False) and the fused kernel agree on the
+    whole path up to fp32 summation order (the fused kernel accumulates the filter rows that feed only one of a step's
+    two conv rows first, then the shared ones as N = 128 MMAs)."""
     fused = phdfx.B200Backbone(backbone, device=0, max_frames=4)
     unfused = phdfx.B200Backbone(backbone, device=0, max_frames=4, fuse_stem_pool=False)
     frames = torch.from_numpy(R.seeded_frames(n, 224, 224, 31)).cuda()
     a = fused.extract_u8(frames, None)
     b = unfused.extract_u8(frames, None)
     assert fused.launches == 41 and unfused.launches == 42
-    assert torch.equal(a, b)
+    err, cos = frame_errors(b.cpu().numpy(), a.cpu().numpy())
+    assert err.max() < 5e-3 and cos.min() > 0.99999
     # separate down-sample launches + residual add (rounds the branch to bf16 first): same features within bf16 noise
     plain = phdfx.B200Backbone(backbone, device=0, max_frames=4, fuse_downsample=False)
     c = plain.extract_u8(frames, None)

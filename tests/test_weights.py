@@ -97,7 +97,12 @@ def test_pack_stem_layout():
 
 def test_pack_stem_pool_layout():
     w = torch.randn(64, 3, 7, 7)
-    p = phdfx.pack_stem_pool(w).to(torch.float32).reshape(7, 4, 64, 8)  # [r][k-chunk][cout][e], k = chunk*8 + e
+    full = phdfx.pack_stem_pool(w).to(torch.float32)
+    assert full.numel() == 7 * 4 * 64 * 8 + 5 * 4 * 128 * 8
+    p = full[:7 * 4 * 64 * 8].reshape(7, 4, 64, 8)  # [r][k-chunk][cout][e], k = chunk*8 + e
+    pairs = full[7 * 4 * 64 * 8:].reshape(5, 4, 128, 8)  # stacked rows for the N = 128 MMAs: [e-2][chunk][e | e-2][8]
+    for e in range(2, 7):
+        assert torch.equal(pairs[e - 2, :, :64], p[e]) and torch.equal(pairs[e - 2, :, 64:], p[e - 2])
     wb = w.to(torch.bfloat16).to(torch.float32)
     for r in (0, 2, 6):
         for s in (0, 3, 6):
