@@ -29,8 +29,8 @@ constexpr int kSpIn = 224, kSpInPitchPx = 232, kSpOut = 112, kSpPool = 56;
 constexpr int kSpRowBytes = kSpInPitchPx * 8;   // 1856
 constexpr int kSpRowPitch = 2048;               // smem pitch of one input row
 constexpr int kSpPairSlots = 16;                // ring of row pairs (2 steps x 2 rows in flight need 7; the rest is prefetch)
-constexpr int kSpBand = 16;                     // conv rows per work item
-constexpr int kSpBandsPerFrame = kSpOut / kSpBand;  // 7
+constexpr int kSpBand = 28;                     // conv rows per work item: 4 bands per frame (1 halo row per 28, and 1024 bands = 6.9 waves of 148 at batch 256)
+constexpr int kSpBandsPerFrame = kSpOut / kSpBand;  // 4
 constexpr int kSpConvRowBytes = kSpOut * 128;   // 14336: one conv row, 112 px x 64 ch bf16
 constexpr int kSpPoolRowBytes = 8192;           // staging pitch (56 x 128 B = 7168 used)
 // weights: [7 filter rows][4 k-chunks][64 cout][8] bf16, then for e = 2..6 the STACKED pairs
