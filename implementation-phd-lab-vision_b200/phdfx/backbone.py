@@ -20,13 +20,22 @@ from . import _lib
 from .weights import Plan, build_plan
 
 
-def jitter_params(fn_idx, brightness: float, contrast: float, saturation: float, hue: float) -> torch.Tensor:
+def jitter_params(fn_idx, brightness: Optional[float] = None, contrast: Optional[float] = None,
+                  saturation: Optional[float] = None, hue: Optional[float] = None, *,
+                  brightness_factor: Optional[float] = None, contrast_factor: Optional[float] = None,
+                  saturation_factor: Optional[float] = None, hue_factor: Optional[float] = None) -> torch.Tensor:
     """One row of K1's colour-jitter parameters from what torchvision's v2 ColorJitter.make_params returns
-    (transforms/v2/_color.py:146-154: fn_idx = randperm(4), the four factors): fp32 [12]."""
+    (transforms/v2/_color.py:146-154: fn_idx = randperm(4), the four factors): fp32 [12].  Accepts the dict as is:
+    jitter_params(**ColorJitter(0.3, 0.3, 0.2, 0.05).make_params([]))."""
+    vals = [brightness if brightness is not None else brightness_factor,
+            contrast if contrast is not None else contrast_factor,
+            saturation if saturation is not None else saturation_factor, hue if hue is not None else hue_factor]
+    if any(v is None for v in vals):
+        raise ValueError("all four factors are required (ColorJitter with every range set, as the reference's)")
     order = [float(int(v)) for v in fn_idx]
     if sorted(order) != [0.0, 1.0, 2.0, 3.0]:
         raise ValueError(f"fn_idx must be a permutation of 0..3, got {list(fn_idx)}")
-    b, c, s, h = float(brightness), float(contrast), float(saturation), float(hue)
+    b, c, s, h = (float(v) for v in vals)
     return torch.tensor(order + [b, c, 1.0 - c, s, 1.0 - s, h, 0.0, 0.0], dtype=torch.float64).to(torch.float32)
 
 

@@ -145,3 +145,23 @@ def test_randomize_bn_matches_oracle_builder(backbone):
     phdfx.randomize_bn_(bb, R.BN_SEED)
     for (n1, p1), (n2, p2) in zip(bb.state_dict().items(), backbone.state_dict().items()):
         assert n1 == n2 and torch.equal(p1, p2), n1
+
+
+def test_jitter_params_row():
+    """phdfx.jitter_params: K1's per-frame colour-jitter row from torchvision's ColorJitter.make_params dict."""
+    import numpy as np
+    from torchvision.transforms import v2 as T2
+
+    torch.manual_seed(3)
+    prm = T2.ColorJitter(brightness=0.3, contrast=0.3, saturation=0.2, hue=0.05).make_params([])
+    row = phdfx.jitter_params(**prm)
+    assert row.dtype == torch.float32 and tuple(row.shape) == (12,)
+    assert [int(v) for v in row[:4]] == [int(v) for v in prm["fn_idx"]]
+    c, s = float(prm["contrast_factor"]), float(prm["saturation_factor"])
+    want = [float(prm["brightness_factor"]), c, 1.0 - c, s, 1.0 - s, float(prm["hue_factor"])]
+    assert np.array_equal(row[4:10].numpy(), np.array(want, dtype=np.float64).astype(np.float32))
+    assert torch.equal(row, phdfx.jitter_params(prm["fn_idx"], prm["brightness_factor"], c, s, prm["hue_factor"]))
+    with pytest.raises(ValueError):
+        phdfx.jitter_params([0, 1, 2, 2], 1.0, 1.0, 1.0, 0.0)
+    with pytest.raises(ValueError):
+        phdfx.jitter_params([0, 1, 2, 3], 1.0, 1.0, 1.0)
