@@ -226,3 +226,28 @@ def test_planned_writing_equals_streaming(tmp_path, n_vars):
         assert (a / f"shard_{sid:05d}.pt").stat().st_size == (b / f"shard_{sid:05d}.pt").stat().st_size
         with open(b / f"shard_{sid:05d}.pt", "rb") as f:
             assert f.read(2) != b"PK"  # legacy (non-zip) pickle, like the reference (:45)
+
+
+def test_plan_shards_property_based(tmp_path_factory):
+    """Random (n_clips, shard_size, shuffle_pool, seed): the integer-only plan always equals what the streaming writer
+    does to tagged records (tiny tensors, so hundreds of cases stay cheap)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(0, 60), shard=st.integers(1, 9), pool=st.integers(1, 25), seed=st.integers(0, 2 ** 31 - 1))
+    def check(n, shard, pool, seed):
+        root = tmp_path_factory.mktemp("plan")
+        w = ShardWriter(root, 1, shard_size=shard, shuffle_pool=pool, shuffle_seed=seed)
+        for i in range(n):
+            meta = {"subject": 1, "action": "a", "cam": "cam_0", "start": i, "end": i + 1, "aug": "orig", "box": None}
+            w.add(ClipRecord([torch.full((1, 4), float(i))], [torch.zeros(1, 17, 3)], [torch.zeros(1, 17, 2)],
+                             [torch.eye(3)], [meta]))
+        index = w.finish(seq_len=1, frame_skip=1, save_fp16=False, augment=False)
+        plan = plan_shards(n, shard, pool, seed)
+        assert [[c["start"] for c in index["clips"] if c["shard_id"] == s] for s in range(index["n_shards"])] == plan
+        assert all(len(p) == shard for p in plan[:-1]) and (not plan or 1 <= len(plan[-1]) <= shard)
+        for sid, ids in enumerate(plan):
+            feats = torch.load(root / f"shard_{sid:05d}.pt", weights_only=True)["feats"]
+            assert feats[:, 0, 0].tolist() == [float(i) for i in ids]
+
+    check()
