@@ -11,7 +11,7 @@ out = torch.empty(n, 2048, device="cuda")
 for _ in range(3):
     eng.extract_u8(frames, None, out=out)
 torch.cuda.synchronize()
-def timeit(fn, reps=30):
+def timeit(fn, reps=100):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
