@@ -57,17 +57,27 @@ def test_b200_backend_refuses_to_run_without_cuda(tmp_path):
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
+TORCH_JOB = ["--synthetic", "10:240x260:230", "--backend", "torch", "--device", "cpu"] + COMMON
+
+
+@pytest.fixture(scope="module")
+def one_process_root(tmp_path_factory):
+    """The reference-path job run once in a single process (shared by both writer modes below)."""
+    a = str(tmp_path_factory.mktemp("w1"))
+    out = run(TORCH_JOB + ["--out", a])
+    assert "packed into 3 shard(s)" in out
+    return a
+
+
 @pytest.mark.parametrize("mode", ["sharded", "gather"])
-def test_torch_backend_one_vs_two_processes(tmp_path, mode):
+def test_torch_backend_one_vs_two_processes(tmp_path, one_process_root, mode):
     """Reference-path run on CPU; the same job split over 2 ranks (gloo) writes the same shards, with the
     shard-parallel writer (every rank writes the shards it owns, no gather: the default) and with the gather-to-rank-0
     writer.  (oneDNN picks batch-size-dependent kernels, so the torch backend is only equal to fp32 rounding across
     splits; the b200 backend is bit-identical — tests/test_entrypoint.py::test_b200_backend_two_ranks_equal_one.)"""
-    a, b = str(tmp_path / "w1"), str(tmp_path / "w2")
-    base = ["--synthetic", "10:240x260:230", "--backend", "torch", "--device", "cpu"] + COMMON
-    out = run(base + ["--out", a])
-    assert "packed into 3 shard(s)" in out
-    out2 = run(base + ["--out", b, "--multi-gpu-writer", mode], nproc=2, port=29533 if mode == "sharded" else 29534)
+    a, b = one_process_root, str(tmp_path / "w2")
+    out2 = run(TORCH_JOB + ["--out", b, "--multi-gpu-writer", mode], nproc=2,
+               port=29533 if mode == "sharded" else 29534)
     assert ("by 2 ranks" in out2) == (mode == "sharded")
     ia, sa = load_root(a)
     ib, sb = load_root(b)
