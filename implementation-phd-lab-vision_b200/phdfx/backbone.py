@@ -162,7 +162,7 @@ class B200Backbone:
 
     def capture_extract(self, frames: torch.Tensor, boxes: Optional[torch.Tensor] = None, flip_w: bool = False,
                         out: Optional[torch.Tensor] = None) -> "ExtractGraph":
-        """Capture extract_u8 on exactly these tensors into a CUDA graph (54 launches -> one graph launch)."""
+        """Capture extract_u8 on exactly these tensors into a CUDA graph (41 launches -> one graph launch)."""
         return ExtractGraph(self, frames, boxes, flip_w, out)
 
     def _check_jitter(self, jitter: torch.Tensor, n: int):

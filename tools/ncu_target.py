@@ -1,6 +1,6 @@
 """Small, deterministic launch sequences for ncu.
 
-    python tools/ncu_target.py step [batch]          # 2 warm-up steps + 1 step of the whole hot path (55 launches each)
+    python tools/ncu_target.py step [batch]          # 2 warm-up steps + 1 step of the whole hot path (41 launches each: K1 + 40 trunk launches)
     python tools/ncu_target.py layers 0,3,5 [batch]  # each listed layer of the execution list twice via phdfx_run_layer
 """
 import sys
