@@ -223,7 +223,8 @@ def test_planned_writing_equals_streaming(tmp_path, n_vars):
         for mx, my in zip(x["meta"], y["meta"]):
             assert {k: v for k, v in mx.items() if k != "box"} == {k: v for k, v in my.items() if k != "box"}
             assert (mx["box"] is None and my["box"] is None) or torch.equal(mx["box"], my["box"])
-        assert (a / f"shard_{sid:05d}.pt").stat().st_size == (b / f"shard_{sid:05d}.pt").stat().st_size
+        # storage keys are decimal renderings of addresses: the sizes may differ by a few digits, not more
+        assert abs((a / f"shard_{sid:05d}.pt").stat().st_size - (b / f"shard_{sid:05d}.pt").stat().st_size) <= 64
         with open(b / f"shard_{sid:05d}.pt", "rb") as f:
             assert f.read(2) != b"PK"  # legacy (non-zip) pickle, like the reference (:45)
 
