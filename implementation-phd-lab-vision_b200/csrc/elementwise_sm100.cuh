@@ -152,6 +152,12 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
       left = boxes[4 * n + 1];
       bh = boxes[4 * n + 2];
       bw = boxes[4 * n + 3];
+      // a box that leaves the frame is cut back to it, as the reference's slicing `frames[:, top:top+h, left:left+w]`
+      // (src/dataset.py:146) cuts it; row staging below is sized from W and relies on left + bw <= W
+      top = min(max(top, 0), H - 1);
+      left = min(max(left, 0), W - 1);
+      bh = min(max(bh, 1), H - top);
+      bw = min(max(bw, 1), W - left);
     }
     const float scale_h = __fdiv_rn(static_cast<float>(bh), static_cast<float>(kImg));
     float sy = __fmaf_rn(scale_h, static_cast<float>(y) + 0.5f, -0.5f);

@@ -38,12 +38,42 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a pipeline bug (lost arrive, wrong tx count) traps instead of hanging the GPU.
+// Spin on an mbarrier phase.  Production builds poll without a bound: measured on B200 (profiles/r02/ab_trap_*.txt),
+// any extra work on the failed-poll path costs throughput — the waiting warps share issue slots and shared-memory
+// bandwidth with the epilogue warps (poll-count trap: +2.1 % on the whole trunk; %globaltimer-based trap: +4.9 %).
+// -DPHDFX_TRAP (debug builds, used while developing a kernel) bounds every wait by TIME (%globaltimer, 20 s) and traps,
+// so a pipeline bug (lost arrive, wrong tx count) ends the kernel instead of hanging the GPU; a legitimately long wait
+// (time-sliced GPU, MPS neighbour, profiler replay) never comes near the bound.
+#ifdef PHDFX_TRAP
+constexpr unsigned long long kMbarTrapNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+#ifndef PHDFX_SPIN_SLEEP_NS
+#define PHDFX_SPIN_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
+#ifdef PHDFX_TRAP
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
+#endif
   do {
+#ifdef PHDFX_WAIT_HINT_NS
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(PHDFX_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred P;\n"
@@ -53,7 +83,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (!done && ++spins > (1u << 26)) __trap();
+#endif
+#if PHDFX_SPIN_SLEEP_NS > 0
+    if (!done) __nanosleep(PHDFX_SPIN_SLEEP_NS);
+#endif
+#ifdef PHDFX_TRAP
+    if (!done && (++spins & 0xFFFFu) == 0) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0)
+        t0 = now;
+      else if (now - t0 > kMbarTrapNs)
+        __trap();
+    }
+#endif
   } while (!done);
 }
 

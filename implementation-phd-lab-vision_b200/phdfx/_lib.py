@@ -29,6 +29,8 @@ EXPORTS = [
     "phdfx_run_layer2",
     "phdfx_chain_span",
     "phdfx_run_chain",
+    "phdfx_set_schedule",
+    "phdfx_get_schedule",
     "phdfx_layer_count",
     "phdfx_layer_info",
     "phdfx_last_launch_count",
@@ -36,6 +38,7 @@ EXPORTS = [
 
 PHDFX_CONV, PHDFX_STEM, PHDFX_MAXPOOL, PHDFX_STEM_POOL = 0, 1, 2, 3
 IMG, IN_WPAD, IN_LPAD, IN_CPAD, FEAT_DIM = 224, 232, 4, 4, 2048
+SCHED_REUSE = 1  # PHDFX_SCHED_REUSE
 JITTER_FLOATS = 12  # one row of phdfx_preprocess_u8_jitter's parameter array
 
 
@@ -117,6 +120,10 @@ def load() -> C.CDLL:
     lib.phdfx_chain_span.argtypes = [vp, i32]
     lib.phdfx_run_chain.restype = i32
     lib.phdfx_run_chain.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
+    lib.phdfx_set_schedule.restype = i32
+    lib.phdfx_set_schedule.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i32, i32]
+    lib.phdfx_get_schedule.restype = i32
+    lib.phdfx_get_schedule.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i32, C.POINTER(C.c_int32)]
     lib.phdfx_layer_count.restype = i32
     lib.phdfx_layer_count.argtypes = [vp]
     lib.phdfx_layer_info.restype = i32

@@ -42,8 +42,11 @@ def jitter_params(fn_idx, brightness: Optional[float] = None, contrast: Optional
 class B200Backbone:
     FEAT_DIM = _lib.FEAT_DIM
 
+    # default frame-wave schedule (phdfx_set_schedule): (first block of the stage | 0 = from the stem, frames per wave)
+    DEFAULT_WAVES = ((0, 0),)
+
     def __init__(self, backbone: nn.Module, device: "int | str | torch.device" = 0, max_frames: int = 1280,
-                 fuse_stem_pool: bool = True, fuse_downsample: bool = True):
+                 fuse_stem_pool: bool = True, fuse_downsample: bool = True, waves=None, reuse: bool = True):
         self._lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("B200Backbone needs a CUDA device (sm_100); this backend has no CPU fallback")
@@ -60,6 +63,43 @@ class B200Backbone:
         _lib.check(
             self._lib.phdfx_load_weights(self._h, w.data_ptr(), w.numel(), b.data_ptr(), b.numel(), arr,
                                          len(self.plan.layers)), self._h)
+        self.set_waves(self.DEFAULT_WAVES if waves is None else waves, reuse=reuse)
+
+    # ---- execution schedule (include/phdfx.h: phdfx_set_schedule) -----------------------------------------------
+    def stage_start(self, after_block: int) -> int:
+        """Execution-list index at which a stage that begins behind bottleneck block `after_block` (1-based; 0 = the
+        stem) starts: the next block's conv1, or its conv2 when that conv1 rides along in the previous block's fused
+        chain launch."""
+        if after_block <= 0:
+            return 0
+        i = self.plan.block_first[after_block]
+        prev_conv2 = self.plan.block_first[after_block - 1] + 1
+        if self.chain_span(prev_conv2) == 3:
+            i += 1
+        return i
+
+    def set_waves(self, waves, reuse: bool = True):
+        """waves: sequence of (after_block, frames_per_wave): the stage that starts behind bottleneck block
+        `after_block` (0 = at the stem; cuts must be in the plan's stage_after_blocks) runs in waves of that many
+        frames (0 = whole call).  E.g. ((0, 32), (7, 0)): stem + layer1 + layer2 in 32-frame waves, the rest at once."""
+        waves = [(int(a), int(w)) for a, w in waves]
+        first = (C.c_int32 * len(waves))(*[self.stage_start(a) for a, _ in waves])
+        wv = (C.c_int32 * len(waves))(*[min(w, self.max_frames) for _, w in waves])
+        _lib.check(self._lib.phdfx_set_schedule(self._h, first, wv, len(waves), _lib.SCHED_REUSE if reuse else 0),
+                   self._h)
+        self.waves, self.reuse = tuple(waves), bool(reuse)
+
+    def set_schedule(self, first_layers, wave_frames, reuse: bool = True):
+        """Raw form: execution-list indices and wave sizes, as phdfx_set_schedule takes them."""
+        first = (C.c_int32 * len(first_layers))(*[int(v) for v in first_layers])
+        wv = (C.c_int32 * len(wave_frames))(*[int(v) for v in wave_frames])
+        _lib.check(self._lib.phdfx_set_schedule(self._h, first, wv, len(first_layers),
+                                                _lib.SCHED_REUSE if reuse else 0), self._h)
+
+    def get_schedule(self):
+        first, wv, fl = (C.c_int32 * 16)(), (C.c_int32 * 16)(), C.c_int32()
+        n = self._lib.phdfx_get_schedule(self._h, first, wv, 16, C.byref(fl))
+        return [(int(first[i]), int(wv[i])) for i in range(n)], int(fl.value)
 
     # ---- nn.Module-shaped surface the reference script touches (:209) ---------------------------------------
     def to(self, *args, **kwargs):

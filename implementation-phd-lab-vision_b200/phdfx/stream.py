@@ -61,6 +61,9 @@ class StreamingExtractor:
             boxes = boxes.to(torch.int32)
             if tuple(boxes.shape) != (n, 4):
                 raise RuntimeError("boxes must be [N,4] (top, left, h, w)")
+            bt, bl, bh, bw = boxes.unbind(1)
+            if bool(((bt < 0) | (bl < 0) | (bh < 1) | (bw < 1) | (bt + bh > H) | (bl + bw > W)).any()):
+                raise RuntimeError(f"boxes must lie inside the {H}x{W} frames (top, left >= 0; h, w >= 1)")
             if not boxes.is_pinned():
                 boxes = boxes.pin_memory()
         if out is None:

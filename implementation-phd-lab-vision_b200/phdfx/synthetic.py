@@ -6,12 +6,51 @@ dataset.py:49-58) and the same per-clip outputs, except that frames stay uint8 a
 next to them — crop / resize / normalise move to the GPU (K1)."""
 from __future__ import annotations
 
+import hashlib
 from dataclasses import dataclass
+from pathlib import Path
 from typing import List, Tuple
 
 import numpy as np
 import torch
 from torch.utils.data import Dataset
+
+WEIGHT_SEED = 0
+BN_SEED = 1
+
+
+def seeded_backbone(weight_seed: int = WEIGHT_SEED, bn_seed: int = BN_SEED):
+    """The reference's trunk construction (src/preprocess_resnet_features.py:207-209) with seeded random init (there
+    is no network for IMAGENET1K_V2) and seeded non-trivial BatchNorm statistics, so BN folding is exercised.
+    Benchmarks and `--synthetic` runs build their weights here; the oracle has its own copy of the same recipe
+    (oracle/resnet50_ref.py) and tests/test_weights.py checks that the two agree tensor for tensor."""
+    import torchvision
+
+    from .weights import randomize_bn_
+
+    torch.manual_seed(weight_seed)
+    resnet = torchvision.models.resnet50(weights=None)
+    backbone = torch.nn.Sequential(*list(resnet.children())[:-1]).eval()
+    return randomize_bn_(backbone, bn_seed)
+
+
+def seeded_frames(n: int, h: int, w: int, seed: int) -> np.ndarray:
+    """uint8 (n,h,w,3) ~ U{0..255}; numpy PCG64, so the bytes are identical on every machine."""
+    return np.random.default_rng(seed).integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+
+
+def csrc_sha() -> str:
+    """Content hash of the kernel sources + the C ABI header (the repo's .git does not travel to the GPU box): stamps
+    profiler captures (tools/ncu_summarize.py) so bench.py can tell whether a committed capture describes the kernels
+    that are running."""
+    root = Path(__file__).resolve().parent.parent
+    files = sorted((root / "csrc").glob("*.cu")) + sorted((root / "csrc").glob("*.cuh"))
+    files.append(root.parent / "include" / "phdfx.h")
+    h = hashlib.sha256()
+    for f in files:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
 
 
 @dataclass

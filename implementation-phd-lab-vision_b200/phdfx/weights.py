@@ -28,6 +28,7 @@ class Plan:
     bias: torch.Tensor  # fp32 [n_bias], CPU, contiguous
     layers: List[LayerDesc]
     names: List[str]  # human-readable layer names, same order as `layers`
+    block_first: List[int] = None  # execution-list index of every bottleneck block's conv1 (16 entries)
 
 
 def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
@@ -84,13 +85,23 @@ def _children(backbone: nn.Module):
                                                             backbone.layer4]
 
 
-def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample: bool = True) -> Plan:
+def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample: bool = True,
+               stage_after_blocks=(3, 7, 13)) -> Plan:
     """fuse_stem_pool=True (default): conv1+bn1+relu+maxpool is ONE launch (stem_pool_sm100.cuh).  False keeps the
     separate implicit-GEMM stem and max-pool kernels (used for A/B measurements and their own parity tests).
     fuse_downsample=True (default): in the first block of each stage the down-sample branch is accumulated into
     conv3's GEMM (K concatenated, weights [cout][width + cin], bias b3 + bd) instead of being a launch and a tensor
-    of its own:  out = relu(conv3(t2) + downsample(x))  (resnet.py:154-161)."""
+    of its own:  out = relu(conv3(t2) + downsample(x))  (resnet.py:154-161).
+    stage_after_blocks: bottleneck blocks (1-based, in network order; default = the ends of layer1, layer2, layer3)
+    after which the execution schedule may be cut into frame-wave stages (phdfx_set_schedule): the tensors that cross
+    such a cut — the block's output and the next block's conv1 output, which a fused chain launch produces on the
+    near side of the cut — get arena buffer ids of their own (6, 7, ...), so every other buffer of a stage can be
+    wave-local scratch (PHDFX_SCHED_REUSE)."""
     conv1, bn1, maxpool, stages = _children(backbone)
+    cuts = set(int(b) for b in stage_after_blocks)
+    next_id = 6
+    carry_t1 = None
+    block_first = []
     chunks, biases, layers, names = [], [], [], []
     w_cursor = 0
     b_cursor = 0
@@ -150,6 +161,14 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample
             cout = blk.conv3.out_channels
             stride = blk.conv2.stride[0]
             t1_buf, t2_buf = (3, 4) if blk_i % 2 == 1 else (4, 3)
+            if carry_t1 is not None:  # first block behind a cut: its conv1 output crosses the cut inside a chain launch
+                t1_buf, carry_t1 = carry_t1, None
+            out_id = o_buf
+            if blk_i in cuts and not last:
+                if next_id + 1 > 15:
+                    raise ValueError("too many stage cuts for the 16 arena buffer ids")
+                out_id, carry_t1, next_id = next_id, next_id + 1, next_id + 2
+            block_first.append(len(layers))
             # conv1 1x1 + bn1 + relu (resnet.py:146-148)
             w, b = fold_conv_bn(blk.conv1, blk.bn1)
             w_off, b_off = add_weights(pack_conv(w), b)
@@ -171,7 +190,7 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample
                 wd, bd = fold_conv_bn(dconv, dbn)
                 wcat = torch.cat([w3.reshape(cout, width), wd.reshape(cout, cin)], dim=1)  # [cout][width | cin]
                 w_off, b_off = add_weights(wcat.contiguous().to(torch.bfloat16).reshape(-1), b3 + bd)
-                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=t2_buf, out_buf=o_buf, res_buf=-1,
+                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=t2_buf, out_buf=out_id, res_buf=-1,
                                    gap=1 if last else 0, in2_buf=x_buf, cin2=cin, stride2=dconv.stride[0], hin2=h,
                                    w_off=w_off, b_off=b_off))
                 names.append(name + ".conv3+downsample")
@@ -187,13 +206,14 @@ def build_plan(backbone: nn.Module, fuse_stem_pool: bool = True, fuse_downsample
                     res_buf = 5
                 # conv3 1x1 + bn3 + residual + relu (:154-161); the last one also fuses avgpool (:278)
                 w_off, b_off = add_weights(pack_conv(w3), b3)
-                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=t2_buf, out_buf=o_buf,
+                layers.append(desc(cin=width, cout=cout, hin=ho, win=ho, relu=1, in_buf=t2_buf, out_buf=out_id,
                                    res_buf=res_buf, gap=1 if last else 0, w_off=w_off, b_off=b_off))
                 names.append(name + ".conv3")
-            x_buf, o_buf = o_buf, x_buf
+            # the block's output is the next block's input; the next output goes to a scratch id (1 / 2) it is not
+            x_buf, o_buf = out_id, (2 if out_id == 1 else 1)
             h = ho
     return Plan(weights=torch.cat(chunks).contiguous(), bias=torch.cat(biases).contiguous(), layers=layers,
-                names=names)
+                names=names, block_first=block_first)
 
 
 def randomize_bn_(backbone: nn.Module, seed: int = 1) -> nn.Module:

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PHDFX_VERSION 102 /* major*100 + minor */
+#define PHDFX_VERSION 103 /* major*100 + minor */
 
 typedef struct phdfx phdfx_t;
 
@@ -143,6 +143,29 @@ int phdfx_run_layer2(phdfx_t* h, int layer_id, const void* d_in, const void* d_i
 int phdfx_chain_span(const phdfx_t* h, int layer_id);
 int phdfx_run_chain(phdfx_t* h, int first_layer_id, const void* d_t1, const void* d_x_or_res, void* d_out,
                     void* d_t1_next, int n, void* stream);
+
+/* Execution schedule: frame waves.  The reference runs every layer over the whole batch before the next one starts
+ * (torchvision models/resnet.py:266-279 under backbone(x), preprocess_resnet_features.py:296); at batch 256 the
+ * activations of the early stages (1.6 MB per frame and layer in layer1) then make a full trip through HBM between any
+ * two launches.  Frames are independent, so the list may instead be cut into consecutive STAGES, each run in waves of
+ * `wave_frames` frames, depth first: stage s processes a wave as soon as stage s-1 has produced its frames, and what one
+ * launch writes is what the next one reads while it is still in the 126 MB L2.  Results are bit-identical for every
+ * schedule (each frame sees the same kernels, tiles and K order).
+ *   first_layer[s]  first execution-list entry of stage s (first_layer[0] = 0, ascending; a stage may not start inside a
+ *                   fused conv2 -> conv3 -> conv1 launch, see phdfx_chain_span); stage s ends where s+1 starts
+ *   wave_frames[s]  frames per wave (0 = the whole call at once); a call's n frames are split into ceil(n / wave)
+ *                   waves of nearly equal size
+ *   flags           PHDFX_SCHED_REUSE: buffers that only hold a stage's intermediates are addressed wave-locally, i.e.
+ *                   every wave rewrites the same wave_frames-sized region (lines are overwritten in L2 before they
+ *                   are ever written back) instead of its own frame range of the arena.  Requires the tensors that
+ *                   enter or leave a wave stage to live in buffer ids that are not used for intermediates
+ *                   (phdfx/weights.py: build_plan(stage_after_blocks=...)); refused otherwise.
+ * With phdfx_extract_u8[_jitter], K1 runs per wave in front of stage 0, so its NHWC4p output is consumed from L2 too.
+ * phdfx_load_weights resets the schedule to one stage without waves.  phdfx_get_schedule returns the stage count and
+ * fills up to `cap` entries. */
+#define PHDFX_SCHED_REUSE 1
+int phdfx_set_schedule(phdfx_t* h, const int32_t* first_layer, const int32_t* wave_frames, int n_stages, int flags);
+int phdfx_get_schedule(const phdfx_t* h, int32_t* first_layer, int32_t* wave_frames, int cap, int* flags);
 
 int phdfx_layer_count(const phdfx_t* h);
 int phdfx_layer_info(const phdfx_t* h, int layer_id, phdfx_layer_desc* out);

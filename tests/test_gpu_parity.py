@@ -286,10 +286,10 @@ def test_chains_are_bit_identical_to_per_conv_kernels(backbone):
     """The fused chain performs the same MMAs in the same order with the same roundings as the three kernels it
     replaces: features are bit-identical with PHDFX_NO_CHAIN=1, at a batch that gives every CTA several tiles."""
     frames = torch.from_numpy(R.seeded_frames(64, 224, 224, 41)).cuda()
-    fused = phdfx.B200Backbone(backbone, device=0, max_frames=64)
+    fused = phdfx.B200Backbone(backbone, device=0, max_frames=64, waves=((0, 0),))
     os.environ["PHDFX_NO_CHAIN"] = "1"
     try:
-        plain = phdfx.B200Backbone(backbone, device=0, max_frames=64)
+        plain = phdfx.B200Backbone(backbone, device=0, max_frames=64, waves=((0, 0),))
     finally:
         del os.environ["PHDFX_NO_CHAIN"]
     a = fused.extract_u8(frames, None)
@@ -487,12 +487,23 @@ def test_full_batch_256_properties():
     equality with the same frames pushed through in small batches, and the native library is what ran."""
     bb = R.seeded_backbone()
     e = phdfx.B200Backbone(bb, device=0, max_frames=256)
-    frames = torch.from_numpy(R.seeded_frames(256, 224, 224, 13)).cuda()
-    big = e.extract_u8(frames, None)
-    # K1 + fused stem/maxpool + 39 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 -> next conv1
-    # chains and layer2's conv2 -> conv3 chains are one launch each), all ours
-    assert e.launches == 41
+    raw = R.seeded_frames(256, 224, 224, 13)
+    frames = torch.from_numpy(raw).cuda()
+    big = e.extract_u8(frames, None)  # the default frame-wave schedule
+    waved_launches = e.launches
+    e.set_waves(((0, 0),))
+    whole = e.extract_u8(frames, None)
+    # un-waved: K1 + fused stem/maxpool + 39 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 ->
+    # next conv1 chains and layer2's conv2 -> conv3 chains are one launch each), all ours
+    assert e.launches == 41 and waved_launches >= 41
+    assert torch.equal(big, whole)
     small = torch.cat([e.extract_u8(frames[i:i + 37].contiguous(), None) for i in range(0, 256, 37)])
     assert torch.equal(big, small)
     assert torch.isfinite(big).all()
+    # and directly against the oracle for a handful of the 256 frames (first, last, and two from the middle waves)
+    pick = [0, 100, 201, 255]
+    x = np.stack([P.crop_resize_normalize(raw[i:i + 1], (0, 0, 224, 224))[0] for i in pick])
+    ref = R.features(x, R.param_list(bb))
+    err, cos = frame_errors(big[pick].cpu().numpy(), ref)
+    assert err.max() <= NORM_TOL and cos.min() >= COS_TOL, (err, cos)
     e.close()

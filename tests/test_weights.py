@@ -165,3 +165,16 @@ def test_jitter_params_row():
         phdfx.jitter_params([0, 1, 2, 2], 1.0, 1.0, 1.0, 0.0)
     with pytest.raises(ValueError):
         phdfx.jitter_params([0, 1, 2, 3], 1.0, 1.0, 1.0)
+
+
+def test_product_and_oracle_build_the_same_seeded_data():
+    """bench.py and `--synthetic` runs take weights / frames from phdfx.synthetic; the oracle keeps its own copy of the
+    recipe (nothing under phdfx/ may import oracle/).  The two must stay the same tensors and bytes."""
+    import numpy as np
+    import resnet50_ref as R
+    from phdfx.synthetic import csrc_sha, seeded_backbone, seeded_frames
+
+    a, b = seeded_backbone().state_dict(), R.seeded_backbone().state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert np.array_equal(seeded_frames(3, 17, 19, 5), R.seeded_frames(3, 17, 19, 5))
+    assert len(csrc_sha()) == 16

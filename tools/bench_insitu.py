@@ -1,7 +1,7 @@
 """In-situ per-launch timing of one trunk pass (phdfx_forward_timed): every launch runs with the L2 contents its
 predecessor left, unlike tools/bench_layers.py (isolated layers, L2 flushed).  Median over repetitions.
 
-    python tools/bench_insitu.py [batch] [reps] > gpurun_out/insitu.json
+    python tools/bench_insitu.py [batch] [reps] [waves, e.g. 0:32,7:0] [reuse 0|1] > gpurun_out/insitu.json
 """
 import json
 import sys
@@ -21,6 +21,9 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 7
     eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
+    if len(sys.argv) > 3:
+        eng.set_waves(tuple(tuple(int(v) for v in st.split(":")) for st in sys.argv[3].split(",")),
+                      reuse=(sys.argv[4] != "0") if len(sys.argv) > 4 else True)
     g = torch.Generator(device="cuda").manual_seed(3)
     xs = [eng.preprocess_u8(torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device="cuda", generator=g))
           for _ in range(3)]

@@ -21,6 +21,9 @@ def main():
     if mode == "step":
         n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
         eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
+        if len(sys.argv) > 3:  # frame-wave schedule, e.g. 0:32,7:0 [reuse 0|1]
+            eng.set_waves(tuple(tuple(int(v) for v in st.split(":")) for st in sys.argv[3].split(",")),
+                          reuse=(sys.argv[4] != "0") if len(sys.argv) > 4 else True)
         frames = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device="cuda")
         for _ in range(3):
             eng.extract_u8(frames, None)
