@@ -706,14 +706,21 @@ int k1_launch(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const in
 int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, const void* ext_in, bool buf0_local,
                float* d_feats, cudaStream_t st, int rev, bool dry, int* span) {
   const auto& L = h->layers[i];
-  auto at = [&](int X) -> char* {
+  // frame f of a tensor lives at base + f * (the TENSOR's bytes per frame) — the dense layout an un-waved pass uses, so
+  // a stage may read what a differently-waved stage wrote; wave-local tensors sit at frame 0 (+ slot) of their buffer
+  auto at = [&](int X, size_t bpf) -> char* {
     if (X < 0) return nullptr;
-    if (X == 0 && ext_in != nullptr)
-      return static_cast<char*>(const_cast<void*>(ext_in)) + static_cast<size_t>(f0) * h->buf_bytes[0];
+    if (X == 0 && ext_in != nullptr) return static_cast<char*>(const_cast<void*>(ext_in)) + static_cast<size_t>(f0) * bpf;
     const bool local = X == 0 ? buf0_local : ((sg.local_mask >> X) & 1u) != 0;
     const size_t fr = local ? static_cast<size_t>(slot) * sg.wave : static_cast<size_t>(f0);
-    return static_cast<char*>(h->bufs[X]) + fr * h->buf_bytes[X];
+    return static_cast<char*>(h->bufs[X]) + fr * bpf;
   };
+  auto in_bpf = [&](const phdfx_layer_desc& l) {
+    return (l.kind == PHDFX_STEM || l.kind == PHDFX_STEM_POOL) ? h->buf_bytes[0]
+                                                              : static_cast<size_t>(l.hin) * l.win * l.cin * 2;
+  };
+  auto in2_bpf = [&](const phdfx_layer_desc& l) { return static_cast<size_t>(l.hin2) * l.hin2 * l.cin2 * 2; };
+  auto out_bpf = [&](const phdfx_layer_desc& l) { return out_elems_per_frame(l) * 2; };
   const bool arena_in = !(L.in_buf == 0 && ext_in != nullptr);
   *span = 1;
   if (h->chain_span[i] > 0) {
@@ -723,11 +730,11 @@ int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, cons
     const auto& c3 = h->layers[i + 1];
     const phdfx_layer_desc* c1 = sp == 3 ? &h->layers[i + 2] : nullptr;
     MapKey k;
-    k.in = at(c2.in_buf);
-    k.in2 = at(c3.in2_buf);
-    k.res = at(c3.res_buf);
-    k.out = at(c3.out_buf);
-    k.t1n = c1 ? at(c1->out_buf) : nullptr;
+    k.in = at(c2.in_buf, in_bpf(c2));
+    k.in2 = at(c3.in2_buf, in2_bpf(c3));
+    k.res = at(c3.res_buf, out_bpf(c3));
+    k.out = at(c3.out_buf, out_bpf(c3));
+    k.t1n = c1 ? at(c1->out_buf, out_bpf(*c1)) : nullptr;
     k.frames = m;
     auto& cache = h->chain_cache[i];
     const ChainPlan* cp = nullptr;
@@ -747,14 +754,15 @@ int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, cons
     }
     return dry ? 0 : launch_chain(h, *cp, m, st, rev);
   }
-  if (L.kind == PHDFX_MAXPOOL) return dry ? 0 : launch_maxpool(h, L, at(L.in_buf), at(L.out_buf), m, st);
+  if (L.kind == PHDFX_MAXPOOL)
+    return dry ? 0 : launch_maxpool(h, L, at(L.in_buf, in_bpf(L)), at(L.out_buf, out_bpf(L)), m, st);
   MapKey k;
   k.frames = m;
-  k.out = L.gap ? nullptr : at(L.out_buf);
+  k.out = L.gap ? nullptr : at(L.out_buf, out_bpf(L));
   if (L.kind != PHDFX_STEM_POOL) {  // the fused stem reads its input through plain bulk copies, not a tensor map
-    k.in = at(L.in_buf);
-    k.in2 = at(L.in2_buf);
-    k.res = at(L.res_buf);
+    k.in = at(L.in_buf, in_bpf(L));
+    k.in2 = at(L.in2_buf, in2_bpf(L));
+    k.res = at(L.res_buf, out_bpf(L));
   }
   auto& cache = h->map_cache[i];
   const LayerMaps* maps = nullptr;
@@ -774,7 +782,7 @@ int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, cons
     maps = &cache.back().maps;
   }
   if (dry) return 0;
-  if (L.kind == PHDFX_STEM_POOL) return launch_stem_pool(h, L, maps->o, at(L.in_buf), m, st);
+  if (L.kind == PHDFX_STEM_POOL) return launch_stem_pool(h, L, maps->o, at(L.in_buf, in_bpf(L)), m, st);
   void* out = L.gap ? static_cast<void*>(d_feats + static_cast<size_t>(f0) * L.cout) : const_cast<void*>(k.out);
   return launch_conv(h, L, *maps, k.res, out, m, st, rev);
 }
@@ -1126,9 +1134,10 @@ int phdfx_set_schedule(phdfx_t* h, const int32_t* first_layer, const int32_t* wa
     stages[s].last = s + 1 < n_stages ? first_layer[s + 1] : nl;
     stages[s].wave = wave_frames[s];
   }
-  if (flags & PHDFX_SCHED_REUSE) {
-    // Which arena buffers may be wave-local in a stage: written inside it and not read after it.  A buffer that carries
-    // a tensor into or out of a stage is addressed by absolute frame number and must not double as scratch.
+  {
+    // Which arena buffers hold only a stage's intermediates: written inside it and not read after it.  A buffer that
+    // carries a tensor into or out of a wave stage keeps frames of OTHER waves alive, so it must not double as
+    // scratch — in either addressing mode (an intermediate of wave j would land on frames of a finished or future wave).
     std::vector<uint32_t> global_mask(n_stages, 0);
     for (int s = 0; s < n_stages; ++s) {
       Stage& sg = stages[s];
@@ -1160,10 +1169,10 @@ int phdfx_set_schedule(phdfx_t* h, const int32_t* first_layer, const int32_t* wa
       live_in &= ~1u;  // buffer 0 (network input) is handled at call time: wave-local only when K1 runs in the waves
       if (live_in & written)
         return fail(h, PHDFX_ERR_INVALID, "stage %d: an input buffer of the stage (mask 0x%x) is rewritten inside it; "
-                    "PHDFX_SCHED_REUSE needs stage inputs in buffers of their own", s, live_in & written);
+                    "a wave stage needs its inputs in buffers of their own", s, live_in & written);
       if (live_out & multi)
         return fail(h, PHDFX_ERR_INVALID, "stage %d: an output buffer of the stage (mask 0x%x) also holds an "
-                    "intermediate; PHDFX_SCHED_REUSE needs stage outputs in buffers of their own", s, live_out & multi);
+                    "intermediate; a wave stage needs its outputs in buffers of their own", s, live_out & multi);
       sg.local_mask = written & ~live_out & ~1u;
       global_mask[s] = live_in | live_out;
     }
@@ -1172,6 +1181,8 @@ int phdfx_set_schedule(phdfx_t* h, const int32_t* first_layer, const int32_t* wa
         if (global_mask[s] & stages[t].local_mask)
           return fail(h, PHDFX_ERR_INVALID, "buffers 0x%x carry tensors across stage %d and are scratch in stage %d",
                       global_mask[s] & stages[t].local_mask, s, t);
+    if (!(flags & PHDFX_SCHED_REUSE))
+      for (auto& sg : stages) sg.local_mask = 0;  // validated above; every tensor addressed by absolute frame number
   }
   h->stages = stages;
   h->sched_flags = flags;

@@ -111,6 +111,22 @@ class SyntheticH36MClips(Dataset):
         rng = np.random.default_rng((self.seed, i, 0))
         return torch.from_numpy(rng.integers(0, 256, size=shape, dtype=np.uint8))
 
+    def fill(self, i: int, out: torch.Tensor) -> None:
+        """Write clip i's frames straight into `out` (uint8 [T,H,W,3], e.g. a slice of a pinned batch buffer): same
+        bytes as frames(i).  fast=True does it in one pass (rotation and XOR fused into the copy; numpy releases the GIL,
+        so several host threads fill different clips at memory speed)."""
+        dst = out.numpy().reshape(-1)
+        if not self.fast:
+            dst[:] = self.frames(i).numpy().reshape(-1)
+            return
+        if self._base is None:
+            self.frames(0)  # builds the base clip
+        base, n = self._base, self._base.size
+        k = (7919 * (i + 1)) % n
+        c = np.uint8((37 * i + 11) & 0xFF)
+        np.bitwise_xor(base[n - k:], c, out=dst[:k])  # np.roll(base, k)[:k] == base[n-k:]
+        np.bitwise_xor(base[:n - k], c, out=dst[k:])
+
     def __getitem__(self, i: int):
         j3, j2, K = self.annotations(i)
         return self.frames(i), j3, j2, K, self.box(i)

@@ -157,9 +157,9 @@ int phdfx_run_chain(phdfx_t* h, int first_layer_id, const void* d_t1, const void
  *                   waves of nearly equal size
  *   flags           PHDFX_SCHED_REUSE: buffers that only hold a stage's intermediates are addressed wave-locally, i.e.
  *                   every wave rewrites the same wave_frames-sized region (lines are overwritten in L2 before they
- *                   are ever written back) instead of its own frame range of the arena.  Requires the tensors that
- *                   enter or leave a wave stage to live in buffer ids that are not used for intermediates
- *                   (phdfx/weights.py: build_plan(stage_after_blocks=...)); refused otherwise.
+ *                   are ever written back) instead of its own frame range of the arena.
+ * Either way the tensors that enter or leave a wave stage must live in buffer ids that are not used for intermediates
+ * (phdfx/weights.py: build_plan(stage_after_blocks=...)); a schedule that would overwrite live frames is refused.
  * With phdfx_extract_u8[_jitter], K1 runs per wave in front of stage 0, so its NHWC4p output is consumed from L2 too.
  * phdfx_load_weights resets the schedule to one stage without waves.  phdfx_get_schedule returns the stage count and
  * fills up to `cap` entries. */

@@ -7,17 +7,23 @@ the engine behind `backbone(x)` (:296): libphdfx.so (hand-written sm_100a kernel
 torch.compile, one process per GPU instead of nn.DataParallel (:214-217), pinned async copies instead of the blocking
 `.cpu()` (:297), and a write-once shard writer.
 
-    python -u src/preprocess_resnet_features.py --root ROOT --out OUT [--augment] ...           # real data (Seam A)
+    python -u src/preprocess_resnet_features.py --root ROOT --out OUT [--augment] ...           # real data
     torchrun --nproc-per-node 8 src/preprocess_resnet_features.py --root ROOT --out OUT ...     # 8 GPUs
     python -u src/preprocess_resnet_features.py --synthetic 64:224x224 --out OUT --weights random:0   # no dataset
 
-With more than one process the default is the shard-parallel writer (--multi-gpu-writer sharded): the shard plan is
-computed up front from (n_clips, shard-size, shuffle-pool, shuffle-seed), rank r extracts the clips of shards
-r, r + world, ... and writes those files itself; rank 0 adds index.pt.  The files hold exactly what a one-process run writes.
+The default writer (--multi-gpu-writer sharded, any number of processes) is the planned one: which clip lands in which
+row of which shard is a pure function of (n_clips, shard-size, shuffle-pool, shuffle-seed), so rank r extracts the
+clips of shards r, r + world, ... in row order and writes those files itself (phdfx/pipeline.py: batch-level host code,
+features downloaded straight into the shard's pinned tensor); rank 0 adds index.pt.  The files hold exactly what the
+reference's streaming writer produces.  --multi-gpu-writer gather keeps the streaming writer on rank 0 behind a
+feature gather (BASELINE config 4's shape).
 
 Real data needs the user's `dataset.py` (the reference's `Human36MPreprocessedClips`, which owns video decoding and
 annotation handling — outside this drop-in) importable, e.g. by running from the reference's src/ directory or with
---dataset-path.  Extra flags: --backend {b200,torch}, --synthetic, --weights, --dataset-path, --max-clips.
+--dataset-path.  With --seam b (default) the dataset only decodes and computes the person box (phdfx/h36m.py wraps the
+user's own methods); crop / resize / normalise and the --augment variants run on the GPU.  --seam a feeds the
+dataset's own CPU-preprocessed fp32 clips to the trunk, as the reference does.
+Extra flags: --backend {b200,torch}, --synthetic, --weights, --dataset-path, --max-clips, --seam, --feed-threads.
 """
 from __future__ import annotations
 
@@ -71,9 +77,14 @@ def parse_args(argv=None):
     p.add_argument("--max-clips", type=int, default=None)
     p.add_argument("--jitter-seed", type=int, default=0, help="seed of the colour-jitter variant (synthetic mode)")
     p.add_argument("--multi-gpu-writer", choices=["sharded", "gather"], default="sharded",
-                   help="world size > 1: 'sharded' = every rank extracts and writes the shards it owns (the shard "
-                        "composition is a pure function of the shuffle parameters; no feature gather), "
-                        "'gather' = contiguous clip ranges per rank, features gathered to rank 0, one writer")
+                   help="'sharded' = every rank extracts and writes the shards it owns (the shard composition is a pure "
+                        "function of the shuffle parameters; no feature gather; also the one-process default), "
+                        "'gather' = contiguous clip ranges per rank, features gathered to rank 0, streaming writer")
+    p.add_argument("--seam", choices=["a", "b"], default="b",
+                   help="real data: b = dataset yields raw uint8 frames + box, GPU does crop/resize/normalise/augment; "
+                        "a = dataset's own CPU preprocessing (fp32 clips), as the reference (forces the streaming writer)")
+    p.add_argument("--feed-threads", type=int, default=4,
+                   help="--synthetic ...:fast only: host threads that generate clips straight into pinned batch buffers")
     return p.parse_args(argv)
 
 
@@ -115,15 +126,30 @@ def dist_setup():
 def real_dataset(args):
     if args.dataset_path:
         sys.path.insert(0, args.dataset_path)
+    import torchvision.io as tvio
+
+    if not hasattr(tvio, "VideoReader"):
+        # torchvision >= 0.24 dropped VideoReader, which the reference's dataset.py imports by name (:14) and only uses
+        # inside a try/except that falls back to torchvision.io.read_video (:323-355): let the import succeed and the
+        # fallback do its job
+        def _no_video_reader(*a, **k):
+            raise RuntimeError("torchvision.io.VideoReader is not available in this torchvision")
+
+        tvio.VideoReader = _no_video_reader
     try:
         from dataset import Human36MPreprocessedClips  # the user's / reference's dataset.py
     except Exception as e:  # noqa: BLE001
         raise RuntimeError(
             "real-data mode needs the reference's dataset.py importable (run from its src/ directory or pass "
             f"--dataset-path); import failed with: {e!r}.  Use --synthetic N to run without a dataset.") from e
-    return Human36MPreprocessedClips(root=args.root, subjects=args.subjects, seq_len=args.seq_len,
-                                     frame_skip=args.frame_skip, stride=args.stride, augment=args.augment,
-                                     max_clips=args.max_clips)
+    base = Human36MPreprocessedClips(root=args.root, subjects=args.subjects, seq_len=args.seq_len,
+                                     frame_skip=args.frame_skip, stride=args.stride,
+                                     augment=args.augment and args.seam == "a", max_clips=args.max_clips)
+    if args.seam == "a":
+        return base
+    from phdfx.h36m import U8ClipDataset
+
+    return U8ClipDataset(base)
 
 
 def parse_synthetic(spec: str, args):
@@ -161,8 +187,7 @@ def main(argv=None):
     n_vars = len(AUG_NAMES) if args.augment else 1
     T = args.seq_len
     out_root = Path(args.out)
-    if is_main:
-        out_root.mkdir(parents=True, exist_ok=True)
+    out_root.mkdir(parents=True, exist_ok=True)  # every rank: the ranks write their own shard files
     log(f"Device     : {device}  (world size {world}, backend {args.backend})")
     log(f"Augment    : {args.augment}  ({'4 variants/clip -> ' + ', '.join(AUG_NAMES) if args.augment else 'none'})")
     log(f"Shard size : {args.shard_size} clips  ({args.shard_size * n_vars} variant entries/shard)")
@@ -170,15 +195,20 @@ def main(argv=None):
     synthetic = args.synthetic is not None
     if not synthetic and not args.root:
         raise SystemExit("either --root or --synthetic is required")
+    if not synthetic and args.multi_gpu_writer == "gather" and args.seam == "b":
+        log("--multi-gpu-writer gather streams clips in dataset order, where frame sizes mix within a batch: using --seam a")
+        args.seam = "a"
     ds = parse_synthetic(args.synthetic, args) if synthetic else real_dataset(args)
     n_clips = len(ds)
+    u8_items = synthetic or args.seam == "b"  # the dataset yields raw uint8 frames + box (Seam B)
+    planned = args.multi_gpu_writer == "sharded" and u8_items
 
     torch_backbone = build_torch_backbone(args.weights)
     if args.backend == "b200":
         import phdfx
 
         frames_per_call = args.batch_size * T
-        backbone = phdfx.B200Backbone(torch_backbone, device=device, max_frames=min(frames_per_call, 1280))
+        backbone = phdfx.B200Backbone(torch_backbone, device=device, max_frames=min(frames_per_call, 2560))
         # host uint8 frames -> host features: pinned, double-buffered H2D / compute / D2H (phdfx/stream.py)
         streamer = phdfx.StreamingExtractor(backbone, batch=min(256, backbone.max_frames))
     else:
@@ -196,66 +226,27 @@ def main(argv=None):
                 return backbone(x).flatten(1).view(Bv, Tt, -1).float()
         return backbone(x).flatten(1).view(Bv, Tt, -1)
 
-    def run_u8(frames: torch.Tensor, boxes: torch.Tensor, flip: bool, to_host: bool = False) -> torch.Tensor:
-        """Seam B: (Bv,T,H,W,3) uint8 + per-clip boxes -> (Bv,T,2048) on the device (to_host: in pinned host memory,
-        through the streaming extractor)."""
-        Bv, Tt, H, W, _ = frames.shape
-        if args.backend == "torch":
-            # the reference's own front end (src/dataset.py:141-152, :166, :242-245), clip by clip
-            import torchvision.transforms.functional as TF
+    extract_fn = make_extract(args, backbone, device, T)
 
-            mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
-            std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
-            vids = []
-            for b in range(Bv):
-                top, left, hh, ww = (int(v) for v in boxes[b])
-                v = frames[b].permute(0, 3, 1, 2)[:, :, top:top + hh, left:left + ww]
-                v = TF.resize(v, [224, 224], antialias=False).to(torch.float32) / 255.0
-                if flip:
-                    v = torch.flip(v, dims=[-1])
-                vids.append((v - mean) / std)
-            return run_normalised(torch.stack(vids))
+    def run_u8(frames: torch.Tensor, boxes: torch.Tensor, flip: bool, to_host: bool = False) -> torch.Tensor:
+        """Seam B (streaming-writer path): (Bv,T,H,W,3) uint8 + per-clip boxes -> (Bv,T,2048) on the device (to_host: in
+        pinned host memory, through the streaming extractor)."""
+        Bv, Tt, H, W, _ = frames.shape
         bx = boxes.to(torch.int32).repeat_interleave(Tt, dim=0)
-        if to_host:  # overlapped copies, features land in pinned host memory
+        if to_host and args.backend == "b200":  # overlapped copies, features land in pinned host memory
             return streamer(frames.view(Bv * Tt, H, W, 3), bx, flip_w=flip).view(Bv, Tt, -1)
         fr = frames.view(Bv * Tt, H, W, 3).to(device, non_blocking=True)
-        return backbone.extract_u8(fr, bx.to(device, non_blocking=True), flip_w=flip).view(Bv, Tt, -1)
+        return extract_fn(fr, bx.to(device, non_blocking=True), flip, None).view(Bv, Tt, -1)
 
     def jitter_variant(frames: torch.Tensor, boxes: torch.Tensor, clip_ids) -> torch.Tensor:
-        """Colour-jitter variant in synthetic mode — the reference's recipe (src/dataset.py:188-198: ColorJitter on the
-        resized [0,1] clip, one draw per clip, then Normalize).  The draw comes from torchvision's own
-        ColorJitter.make_params under a per-clip seed; with --backend b200 the ops run inside K1
-        (phdfx_extract_u8_jitter), with --backend torch torchvision applies them."""
-        import torch.nn.functional as F
-        from torchvision.transforms import v2 as T2
-
-        jit = T2.ColorJitter(brightness=0.3, contrast=0.3, saturation=0.2, hue=0.05)
+        """Colour-jitter variant — the reference's recipe (src/dataset.py:188-198: ColorJitter on the resized [0,1]
+        clip, one draw per clip, then Normalize) with the per-clip draws of jitter_rows; b200: inside K1
+        (phdfx_extract_u8_jitter), torch: torchvision's own ops."""
         Bv, Tt, H, W, _ = frames.shape
-        if args.backend == "b200":
-            import phdfx
-
-            rows = []
-            for b in range(Bv):
-                torch.manual_seed(args.jitter_seed * 1_000_003 + int(clip_ids[b]))
-                prm = jit.make_params([])
-                rows.append(phdfx.jitter_params(prm["fn_idx"], prm["brightness_factor"], prm["contrast_factor"],
-                                                prm["saturation_factor"], prm["hue_factor"]))
-            jrows = torch.stack(rows).repeat_interleave(Tt, dim=0).to(device, non_blocking=True)
-            fr = frames.view(Bv * Tt, H, W, 3).to(device, non_blocking=True)
-            bx = boxes.to(torch.int32).repeat_interleave(Tt, dim=0).to(device, non_blocking=True)
-            return backbone.extract_u8(fr, bx, jitter=jrows).view(Bv, Tt, -1)
-        mean = torch.tensor(IMAGENET_MEAN, device=device).view(1, 3, 1, 1)
-        std = torch.tensor(IMAGENET_STD, device=device).view(1, 3, 1, 1)
-        outs = []
-        for b in range(Bv):
-            top, left, hh, ww = (int(v) for v in boxes[b])
-            crop = frames[b, :, top:top + hh, left:left + ww].to(device).permute(0, 3, 1, 2).float()
-            if (hh, ww) != (224, 224):
-                crop = F.interpolate(crop, size=(224, 224), mode="bilinear", align_corners=False).round()
-            torch.manual_seed(args.jitter_seed * 1_000_003 + int(clip_ids[b]))
-            vid = jit(crop / 255.0)
-            outs.append((vid - mean) / std)
-        return run_normalised(torch.stack(outs))
+        jrows = jitter_rows(args.jitter_seed, clip_ids).repeat_interleave(Tt, dim=0).to(device, non_blocking=True)
+        fr = frames.view(Bv * Tt, H, W, 3).to(device, non_blocking=True)
+        bx = boxes.to(torch.int32).repeat_interleave(Tt, dim=0).to(device, non_blocking=True)
+        return extract_fn(fr, bx, False, jrows).view(Bv, Tt, -1)
 
     def extract_clips(ids, items, to_host: bool = False):
         """Features + annotations of the clips `ids` (dataset numbers; `items` = what the dataset returned for them,
@@ -265,7 +256,7 @@ def main(argv=None):
         small = []  # per clip: (joints3d[v], joints2d[v], K[v], box)
         if not ids:
             return feats.to(feat_dtype), small
-        if synthetic:
+        if u8_items:
             frames, boxes, items = items  # (Bv,T,H,W,3) uint8, (Bv,4), per-clip tuples without the frames
             host = to_host and args.backend == "b200"
             f_orig = run_u8(frames, boxes, False, to_host=host)
@@ -285,18 +276,15 @@ def main(argv=None):
                 else:
                     small.append(([j3], [j2], [K], box))
         else:
-            if args.augment:  # item = list of 4 (video, j3d, j2d, K) variants (src/dataset.py:411-426)
-                vids = [torch.stack([it[v][0] for it in items]) for v in range(n_vars)]
+            # Seam A: clips were stacked per variant in the loader's workers (_collate_seam_a) and pinned by its
+            # pin-memory thread, so the copies below are asynchronous (the reference collates in its workers too, :59-69)
+            vids, small = items
+            if args.augment:  # variants as src/dataset.py:411-426 builds them
                 f = [run_normalised(vids[0]), run_normalised(vids[1]), run_normalised(vids[2])]
                 f.append(torch.flip(f[0], dims=[1]))  # trev == reversed orig (dataset.py:201-207)
                 feats = torch.stack(f, dim=1)
-                for it in items:
-                    small.append(([it[v][1] for v in range(4)], [it[v][2] for v in range(4)],
-                                  [it[v][3] for v in range(4)], None))
             else:
-                feats = run_normalised(torch.stack([it[0] for it in items])).unsqueeze(1)
-                for it in items:
-                    small.append(([it[1]], [it[2]], [it[3]], it[4]))
+                feats = run_normalised(vids[0]).unsqueeze(1)
         feats = feats.to(feat_dtype)
         return (feats.cpu() if to_host else feats), small
 
@@ -309,10 +297,10 @@ def main(argv=None):
             from torch.utils.data import DataLoader
 
             loader = iter(DataLoader(ds, batch_sampler=live, num_workers=min(args.num_workers, len(live)),
-                                     collate_fn=_collate_synthetic if synthetic else _collate_list,
+                                     collate_fn=_collate_synthetic if u8_items else _collate_seam_a,
                                      pin_memory=torch.cuda.is_available(), prefetch_factor=2))
         else:
-            loader = ((_collate_synthetic if synthetic else _collate_list)([ds[i] for i in b]) for b in live)
+            loader = ((_collate_synthetic if u8_items else _collate_seam_a)([ds[i] for i in b]) for b in live)
         for b in batches:
             yield b, (next(loader) if b else None)
 
@@ -327,28 +315,34 @@ def main(argv=None):
 
     B = args.batch_size
     t_all = time.time()
-    if world > 1 and args.multi_gpu_writer == "sharded":
-        # ---- shard-parallel: no feature gather, every rank writes the shard files it owns ------------------------
-        import torch.distributed as dist
+    if planned:
+        # ---- planned writer: every rank extracts the shards it owns, in row order, and writes them itself -----------
+        from phdfx.pipeline import ClipFeeder, PlannedShardRun
 
         plan = plan_shards(n_clips, args.shard_size, args.shuffle_pool, args.shuffle_seed)
-        aw = AsyncShardWriter()
         mine = list(range(rank, len(plan), world))
-        parts = [(sid, plan[sid][c0:c0 + B]) for sid in mine for c0 in range(0, len(plan[sid]), B)]
-        fetched = clip_batches([p for _, p in parts])
-        for k, sid in enumerate(mine):
-            ids = plan[sid]
-            groups = []
-            while len(groups) < len(ids):
-                part, items = next(fetched)
-                host, small = extract_clips(part, items, to_host=True)
-                groups.extend(clip_record(i, host[j], small[j]) for j, i in enumerate(part))
-            aw.save(assemble_shard(groups, n_vars), shard_path(out_root, sid))
-            log(f"[{100 * (k + 1) / max(1, len(mine)):5.1f}%] rank 0: shard {sid} ({len(ids)} clips) queued "
-                f"| {time.time() - t_all:6.1f}s")
-        aw.wait()
-        aw.stop()
-        dist.barrier()
+        if is_main:  # shard files of an earlier run with a different plan would sit next to the new index
+            for old in sorted(out_root.glob("shard_*.pt")):
+                try:
+                    if int(old.stem.split("_")[1]) >= len(plan):
+                        log(f"removing stale {old.name} (this run writes {len(plan)} shard(s))")
+                        old.unlink()
+                except (ValueError, OSError):
+                    pass
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        run = PlannedShardRun(extract=make_extract(args, backbone, device, T), device=device, out_root=out_root,
+                              n_vars=n_vars, seq_len=T, feat_dtype=feat_dtype, augment=args.augment,
+                              jitter_rows=lambda ids: jitter_rows(args.jitter_seed, ids),
+                              clip_meta=lambda i: ds.index[i], log=log)
+        threads = args.feed_threads if (synthetic and getattr(ds, "fast", False)) else 0
+        st = run.run(lambda batches: ClipFeeder(ds, batches, workers=args.num_workers,
+                                                pin=device.type == "cuda", threads=threads),
+                     plan, mine, B)
+        if world > 1:
+            dist.barrier()
         if is_main:
             index = index_from_plan(plan, lambda i: ds.index[i], n_vars, args.seq_len, args.frame_skip,
                                     args.save_fp16, args.augment, args.shuffle_seed, args.shuffle_pool)
@@ -358,8 +352,14 @@ def main(argv=None):
             log(f"Done: {n_clips} clips x {n_vars} variant(s) packed into {len(plan)} shard(s) by {world} ranks")
             log(f"Total time {total:.1f}s | {n_clips / max(total, 1e-9):.1f} clips/s "
                 f"({n_clips * n_vars * T / max(total, 1e-9):.0f} frames/s)")
-        dist.barrier()
-        dist.destroy_process_group()
+            log(f"rank 0 loop: {st.clips} clips, {st.frames_computed} frames through the trunk in {st.total_s:.2f}s "
+                f"({st.frames_computed / max(st.total_s, 1e-9):.0f} computed frames/s, "
+                f"{st.clips * n_vars * T / max(st.total_s, 1e-9):.0f} written frames/s) | waited {st.feed_wait_s:.2f}s "
+                f"for frames, {st.writer_wait_s:.2f}s for the writer | writer: {st.bytes_written / 1e6:.0f} MB in "
+                f"{st.write_s:.2f}s ({st.bytes_written / 1e6 / max(st.write_s, 1e-9):.0f} MB/s, overlapped)")
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
 
     writer = ShardWriter(out_root, n_vars, args.shard_size, args.shuffle_pool, args.shuffle_seed) if is_main else None
@@ -413,6 +413,59 @@ def main(argv=None):
         dist.destroy_process_group()
 
 
+def jitter_rows(jitter_seed: int, clip_ids) -> torch.Tensor:
+    """One row of colour-jitter parameters per clip (fp32 [B,12], phdfx.jitter_params layout): the draw torchvision's own
+    ColorJitter(0.3, 0.3, 0.2, 0.05).make_params makes (the reference's recipe, src/dataset.py:188-198, one draw per
+    clip) under a per-clip seed, so a run is reproducible and independent of how clips are batched or sharded."""
+    from torchvision.transforms import v2 as T2
+
+    from phdfx.backbone import jitter_params
+
+    jit = T2.ColorJitter(brightness=0.3, contrast=0.3, saturation=0.2, hue=0.05)
+    rows = []
+    for i in clip_ids:
+        torch.manual_seed(jitter_seed * 1_000_003 + int(i))
+        prm = jit.make_params([])
+        rows.append(jitter_params(prm["fn_idx"], prm["brightness_factor"], prm["contrast_factor"],
+                                  prm["saturation_factor"], prm["hue_factor"]))
+    return torch.stack(rows)
+
+
+def make_extract(args, backbone, device, T):
+    """extract(frames [N,H,W,3] uint8, boxes [N,4] int32, flip, jitter [N,12] | None) -> fp32 [N,2048], all on `device`
+    (phdfx/pipeline.py).  b200: one call into libphdfx (K1 + trunk).  torch: the reference's own front end clip by clip
+    (src/dataset.py:141-152, :166, :188-198, :242-245) and its eager trunk — the comparison arm."""
+    if args.backend == "b200":
+        return lambda frames, boxes, flip, jitter: backbone.extract_u8(frames, boxes, flip_w=flip, jitter=jitter)
+
+    import torchvision.transforms.functional as TF
+    from torchvision.transforms.v2 import functional as F2
+
+    mean = torch.tensor(IMAGENET_MEAN, device=device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, device=device).view(1, 3, 1, 1)
+    ops = (F2.adjust_brightness, F2.adjust_contrast, F2.adjust_saturation, F2.adjust_hue)
+
+    def extract(frames, boxes, flip, jitter):
+        vids = []
+        for c0 in range(0, frames.shape[0], T):
+            top, left, hh, ww = (int(v) for v in boxes[c0])
+            v = frames[c0:c0 + T].permute(0, 3, 1, 2)[:, :, top:top + hh, left:left + ww]
+            v = TF.resize(v, [224, 224], antialias=False).to(torch.float32) / 255.0
+            if jitter is not None:  # ColorJitter.transform with the given draw (transforms/v2/_color.py:156-173)
+                row = jitter[c0].tolist()
+                factor = {0: row[4], 1: row[5], 2: row[7], 3: row[9]}
+                for k in range(4):
+                    v = ops[int(row[k])](v, factor[int(row[k])])
+            if flip:
+                v = torch.flip(v, dims=[-1])
+            vids.append((v - mean) / std)
+        x = torch.cat(vids).to(device)
+        with torch.autocast(device_type=device.type, dtype=torch.bfloat16, enabled=device.type == "cuda"):
+            return backbone(x).flatten(1).float()
+
+    return extract
+
+
 def _augment_annotations(j3, j2, K):
     """Annotation side of the four variants (src/dataset.py:158-207): hflip mirrors x and swaps left/right joints."""
     flip_pairs = [(1, 4), (2, 5), (3, 6), (14, 11), (15, 12), (16, 13)]  # src/dataset.py:39-46
@@ -426,9 +479,16 @@ def _augment_annotations(j3, j2, K):
     return ([j3, j3, j3f, torch.flip(j3, dims=[0])], [j2, j2, j2f, torch.flip(j2, dims=[0])], [K, K, Kf, K], None)
 
 
-def _collate_list(batch):
-    """Real-dataset clips stay a list of per-clip items (src/dataset.py:403-437 return types)."""
-    return batch
+def _collate_seam_a(batch):
+    """Seam A clips (the reference dataset's own items, src/dataset.py:403-437), collated in the worker: one stacked
+    fp32 tensor per computed variant (so the loader's pin-memory thread page-locks whole batches) + per-clip
+    annotations.  The time-reversed variant's pixels are dropped here: its features are the reversed `orig` features."""
+    if isinstance(batch[0], list):  # --augment: 4 x (video, j3d, j2d, K)
+        vids = [torch.stack([it[v][0] for it in batch]) for v in range(3)]
+        small = [([it[v][1] for v in range(4)], [it[v][2] for v in range(4)], [it[v][3] for v in range(4)], None)
+                 for it in batch]
+        return vids, small
+    return [torch.stack([it[0] for it in batch])], [([it[1]], [it[2]], [it[3]], it[4]) for it in batch]
 
 
 def _collate_synthetic(batch):

@@ -100,10 +100,11 @@ def test_unsafe_schedules_are_refused(eng256):
         e2 = phdfx.B200Backbone(bb, device=0, max_frames=64)
     finally:
         phdfx.backbone.build_plan = orig
-    with pytest.raises(RuntimeError, match="buffers of their own|scratch"):
-        e2.set_waves(((0, 16), (7, 0)), reuse=True)
     frames = torch.from_numpy(R.seeded_frames(64, 224, 224, 3)).cuda()
     ref = e2.extract_u8(frames, None).clone()
-    e2.set_waves(((0, 16), (7, 0)), reuse=False)  # absolute addressing is always safe
-    assert torch.equal(e2.extract_u8(frames, None), ref)
+    for reuse in (True, False):  # intermediates of one wave would land on live frames of another, in either mode
+        with pytest.raises(RuntimeError, match="buffers of their own|scratch"):
+            e2.set_waves(((0, 16), (7, 0)), reuse=reuse)
+    assert torch.equal(e2.extract_u8(frames, None), ref)  # the refused call left the schedule alone
+    assert torch.equal(e2.extract_u8(frames, None), eng256.extract_u8(frames, None))  # cut and un-cut plans agree
     e2.close()
