@@ -92,6 +92,7 @@ struct phdfx {
   bool use_cg2 = true;              // PHDFX_NO_CG2=1: keep the K-heavy layers on the 1-CTA kernel
   bool use_rev = true;              // PHDFX_NO_REV=1: every launch walks its tiles in ascending order
   bool use_halo = true;             // PHDFX_NO_HALO=1: 3x3/1 convs of layer1 / layer2 through the im2col path
+  bool use_small_n = true;          // PHDFX_NO_SMALL_N=1: keep 256-wide N tiles for launches with few tiles
   std::vector<int> chain_span;      // per layer: layers covered by the fused launch STARTING there (0 = none)
   std::vector<Stage> stages;        // execution schedule (default: one stage, no waves)
   int sched_flags = 0;
@@ -182,7 +183,11 @@ struct Geo {
   bool cg2;        // run on CTA pairs (tcgen05 cta_group::2): each SM loads half of the 256-row weight tile
 };
 
-Geo geometry(const phdfx_t* h, const phdfx_layer_desc& L) {
+// `frames`: frames in the launch (0 = a large launch).  Small launches get narrower N tiles: with fewer tiles than SMs
+// the time of a K-heavy layer is the time ONE CTA needs to stream its K x BN weight slab (2.4 MB for layer4's 3x3 at
+// BN = 256), so the output channels are spread over up to 4x more CTAs.  Each output element still accumulates the
+// same products in the same K order, so results do not depend on the choice (bit-identical across batch sizes).
+Geo geometry(const phdfx_t* h, const phdfx_layer_desc& L, int frames = 0) {
   const bool use_halo = h ? h->use_halo : true, use_cg2 = h ? h->use_cg2 : true;
   Geo g{};
   g.P = (L.hin + 2 * L.pad - L.r) / L.stride + 1;
@@ -206,6 +211,10 @@ Geo geometry(const phdfx_t* h, const phdfx_layer_desc& L) {
     } else
       g.mode = MODE_IM2COL;
     g.bn = L.cout >= 256 ? 256 : L.cout;
+    if (frames > 0 && h && h->use_small_n && !L.gap && g.mode != MODE_HALO) {
+      const long long m_tiles = (static_cast<long long>(frames) * g.P * g.Q + kBlockM - 1) / kBlockM;
+      while (g.bn > 64 && m_tiles * (L.cout / g.bn) * 2 <= h->num_sms) g.bn /= 2;
+    }
     g.cg2 = use_cg2 && (g.mode == MODE_TILED || g.mode == MODE_IM2COL) && g.bn == 256 && L.res_buf < 0 &&
             !L.gap && g.num_kb >= 8;
   }
@@ -281,7 +290,7 @@ void im2col_small_tensor_fixup(CUtensorMap* m, size_t bytes) {
 
 int build_maps(phdfx_t* h, const phdfx_layer_desc& L, const void* in, const void* in2, const void* res, void* outp,
                int frames, LayerMaps* out, bool arena = false) {
-  const Geo g = geometry(h, L);
+  const Geo g = geometry(h, L, frames);
   const __nv_bfloat16* w = h->d_weights + L.w_off;
   memset(&out->o, 0, sizeof(CUtensorMap));
   memset(&out->r, 0, sizeof(CUtensorMap));
@@ -426,7 +435,7 @@ int launch_conv_cg2_t(phdfx_t* h, const LayerMaps& maps, const ConvParams& p, cu
 int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, const void* res, void* out, int n,
                 cudaStream_t st, int rev = 0, long long* trace = nullptr) {
   const bool has_res = res != nullptr;
-  const Geo g = geometry(h, L);
+  const Geo g = geometry(h, L, n);
   ConvParams p{};
   p.Cout = L.cout;
   p.num_kb = g.num_kb;
@@ -830,6 +839,7 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   if (const char* e = getenv("PHDFX_NO_HALO")) h->use_halo = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_CG2")) h->use_cg2 = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_REV")) h->use_rev = !(e[0] == '1');
+  if (const char* e = getenv("PHDFX_NO_SMALL_N")) h->use_small_n = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_SM_CAP")) {  // experiments: run every persistent grid on fewer SMs
     const int cap = atoi(e);
     if (cap >= 2 && cap < h->num_sms) h->num_sms = cap & ~1;

@@ -47,6 +47,17 @@ constexpr int kJitterFloats = 12;
 enum K1Kind : int { KIND_PLAIN = 0, KIND_JITTER_SUMS = 1, KIND_JITTER = 2 };
 
 __device__ __forceinline__ float jit_clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+// a / b given rb = RN(1 / b): Markstein's correction sequence (q0 = a*rb; e = a - b*q0 exactly, by FMA; q = q0 + e*rb).
+// With a correctly rounded reciprocal this IS the correctly rounded quotient (__fdiv_rn) for every operand pair the
+// colour ops produce (normal range, |a| <= |b| <= 1 or constant b), at 3 instructions instead of the ~20 of an IEEE
+// division — the jitter variant of K1 is bound by its 10 divisions per pixel, not by memory.  Divisors whose
+// significand is all ones (where the bound of the theorem is not met) can differ in the last fp32 bit; the bf16
+// rounding that follows hides all but ~2^-15 of those.
+__device__ __forceinline__ float div_by(float a, float b, float rb) {
+  const float q0 = __fmul_rn(a, rb);
+  const float e = __fmaf_rn(-b, q0, a);
+  return __fmaf_rn(e, rb, q0);
+}
 __device__ __forceinline__ float jit_gray(const float (&c)[3]) {
   return __fmaf_rn(c[2], 0.114f, __fmaf_rn(c[1], 0.587f, __fmul_rn(c[0], 0.2989f)));
 }
@@ -59,16 +70,19 @@ __device__ __forceinline__ void jit_hue(float (&c)[3], float hue) {
   const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
   const bool eqc = maxc == minc;
   const float cr = __fsub_rn(maxc, minc);
-  const float s = __fdiv_rn(cr, eqc ? 1.0f : maxc);
+  const float sdiv = eqc ? 1.0f : maxc;
+  const float s = div_by(cr, sdiv, __frcp_rn(sdiv));
   const float div = eqc ? 1.0f : cr;
-  const float rc = __fdiv_rn(__fsub_rn(maxc, r), div), gc = __fdiv_rn(__fsub_rn(maxc, g), div),
-              bc = __fdiv_rn(__fsub_rn(maxc, b), div);
+  const float rdiv = __frcp_rn(div);  // one reciprocal for the three channel ratios
+  const float rc = div_by(__fsub_rn(maxc, r), div, rdiv), gc = div_by(__fsub_rn(maxc, g), div, rdiv),
+              bc = div_by(__fsub_rn(maxc, b), div, rdiv);
   const bool neq_r = maxc != r, eq_g = maxc == g;
   const float hg = (eq_g && neq_r) ? __fsub_rn(__fadd_rn(rc, 2.0f), bc) : 0.0f;
   const float hr = (!neq_r) ? __fsub_rn(bc, gc) : 0.0f;
   const float hb = (neq_r && !eq_g) ? __fsub_rn(__fadd_rn(gc, 4.0f), rc) : 0.0f;
   float h = __fadd_rn(__fadd_rn(hr, hg), hb);
-  h = fmodf(__fadd_rn(__fmul_rn(h, 1.0f / 6.0f), 1.0f), 1.0f);
+  h = __fadd_rn(__fmul_rn(h, 1.0f / 6.0f), 1.0f);  // in [5/6, 11/6]: fmod(x, 1) == x - floor(x), exactly
+  h = __fsub_rn(h, floorf(h));
   h = __fadd_rn(h, hue);              // h.add_(hue_factor).remainder_(1.0): result takes the divisor's sign
   h = __fsub_rn(h, floorf(h));
   if (h >= 1.0f) h = 0.0f;
@@ -123,6 +137,7 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
   griddep_wait();  // the arena input buffer may still be read by the previous step's stem kernel
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  const float rstd[3] = {__frcp_rn(0.229f), __frcp_rn(0.224f), __frcp_rn(0.225f)};  // jitter kinds: div_by()
   const int row_cap = (3 * W + 32 + 15) & ~15;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -249,7 +264,7 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
           jit_apply(px, prm, mean_gray, false);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const __nv_bfloat16 hv = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(px[c], mean[c]), stdv[c]));
+            const __nv_bfloat16 hv = __float2bfloat16_rn(div_by(__fsub_rn(px[c], mean[c]), stdv[c], rstd[c]));
             r[c] = *reinterpret_cast<const uint16_t*>(&hv);
           }
         }

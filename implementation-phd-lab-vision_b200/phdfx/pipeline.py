@@ -123,18 +123,21 @@ class ClipFeeder:
             if prev is not None and prev.copied is not None:
                 prev.copied.synchronize()  # the slot's previous frames have been uploaded
             buf = slots[sl][:len(ids)]
-            futs = [pool.submit(self.ds.fill, i, buf[j]) for j, i in enumerate(ids)]
+            futs = [pool.submit(one, i, buf[j]) for j, i in enumerate(ids)]
             return k, ids, buf, futs
+
+        def one(i, out):  # frames into the pinned slot, annotations alongside: all off the main thread
+            self.ds.fill(i, out)
+            return self.ds.annotations(i), self.ds.box(i)
 
         pending = [build(k) for k in range(min(self.depth, len(self.batches)))]
         nxt = len(pending)
         try:
             while pending:
                 k, ids, buf, futs = pending.pop(0)
-                for f in futs:
-                    f.result()
-                ann = [self.ds.annotations(i) for i in ids]
-                boxes = torch.stack([self.ds.box(i) for i in ids]).to(torch.int64)
+                res = [f.result() for f in futs]
+                ann = [r[0] for r in res]
+                boxes = torch.stack([r[1] for r in res]).to(torch.int64)
                 cb = ClipBatch(ids, [(torch.arange(len(ids)), buf, boxes)], torch.stack([a[0] for a in ann]),
                                torch.stack([a[1] for a in ann]), torch.stack([a[2] for a in ann]), boxes)
                 handed[k % len(slots)] = cb

@@ -83,8 +83,9 @@ def parse_args(argv=None):
     p.add_argument("--seam", choices=["a", "b"], default="b",
                    help="real data: b = dataset yields raw uint8 frames + box, GPU does crop/resize/normalise/augment; "
                         "a = dataset's own CPU preprocessing (fp32 clips), as the reference (forces the streaming writer)")
-    p.add_argument("--feed-threads", type=int, default=4,
-                   help="--synthetic ...:fast only: host threads that generate clips straight into pinned batch buffers")
+    p.add_argument("--feed-threads", type=int, default=-1,
+                   help="--synthetic ...:fast only: host threads that generate clips straight into pinned batch buffers "
+                        "(-1 = min(8, cpus / world size), 0 = use the DataLoader workers instead)")
     return p.parse_args(argv)
 
 
@@ -337,7 +338,8 @@ def main(argv=None):
                               n_vars=n_vars, seq_len=T, feat_dtype=feat_dtype, augment=args.augment,
                               jitter_rows=lambda ids: jitter_rows(args.jitter_seed, ids),
                               clip_meta=lambda i: ds.index[i], log=log)
-        threads = args.feed_threads if (synthetic and getattr(ds, "fast", False)) else 0
+        threads = args.feed_threads if args.feed_threads >= 0 else max(2, min(8, (os.cpu_count() or 8) // world))
+        threads = threads if (synthetic and getattr(ds, "fast", False)) else 0
         st = run.run(lambda batches: ClipFeeder(ds, batches, workers=args.num_workers,
                                                 pin=device.type == "cuda", threads=threads),
                      plan, mine, B)

@@ -507,3 +507,65 @@ def test_full_batch_256_properties():
     err, cos = frame_errors(big[pick].cpu().numpy(), ref)
     assert err.max() <= NORM_TOL and cos.min() >= COS_TOL, (err, cos)
     e.close()
+
+
+def test_config5_fixture_is_what_head_extracts(golden_dir):
+    """BASELINE config 5 is checked on CPU (tests/test_e2e_loss.py) against features a B200 extracted earlier
+    (tests/golden/e2e_b200_feats.npz, tools/e2e_extract.py).  Re-extract the same clips with the library under test:
+    within the north-star tolerance always, and bit for bit when the fixture was made from these very kernel sources."""
+    from phdfx.synthetic import SyntheticH36MClips, csrc_sha
+
+    fx = np.load(os.path.join(golden_dir, "e2e_b200_feats.npz"))
+    n_clips, seq_len, H, W, side, seed = (int(v) for v in fx["cfg"])
+    ds = SyntheticH36MClips(n_clips, seq_len=seq_len, height=H, width=W, subjects=(1, 6, 7, 8), seed=seed,
+                            box_side=side)
+    e = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n_clips * seq_len)
+    fr = torch.stack([ds.frames(i) for i in range(n_clips)]).view(n_clips * seq_len, H, W, 3).cuda()
+    bx = torch.stack([ds.box(i) for i in range(n_clips)]).to(torch.int32).repeat_interleave(seq_len, dim=0).cuda()
+    got = e.extract_u8(fr, bx).cpu().numpy()
+    want = fx["feats"].reshape(-1, 2048)
+    err, cos = frame_errors(got, want)
+    assert err.max() <= NORM_TOL and cos.min() >= COS_TOL, (err.max(), cos.min())
+    same_sources = "csrc_sha" in fx and str(fx["csrc_sha"]) == csrc_sha()
+    if same_sources:
+        assert np.array_equal(got, want), "fixture was extracted from these sources but the bits differ"
+    print(f"config-5 fixture vs HEAD: norm_err {err.max():.2e} min cos {cos.min():.7f} "
+          f"bit_identical {np.array_equal(got, want)} same_sources {same_sources}")
+    e.close()
+
+
+@pytest.mark.parametrize("switch,exact", [("PHDFX_NO_CG2", True), ("PHDFX_NO_REV", True), ("PHDFX_NO_SMALL_N", True),
+                                          ("PHDFX_NO_HALO", False)])
+def test_kernel_selection_switches(backbone, switch, exact):
+    """The A/B switches select other kernels for the same layers (1-CTA instead of CTA-pair implicit GEMM, ascending tile
+    order, 256-wide N tiles for small launches, im2col instead of the halo patch mode).  They are read per handle at
+    phdfx_create.  All but NO_HALO keep every output element's K order, hence bit-identical features; the im2col path
+    walks K tap-major instead of channel-block-major, so layer2's 3x3 convs round differently (fp32 accumulation)."""
+    base = phdfx.B200Backbone(backbone, device=0, max_frames=40)
+    os.environ[switch] = "1"
+    try:
+        alt = phdfx.B200Backbone(backbone, device=0, max_frames=40)
+    finally:
+        del os.environ[switch]
+    again = phdfx.B200Backbone(backbone, device=0, max_frames=40)  # created after the switch was removed: default kernels
+    for n in (1, 3, 8, 37):
+        frames = torch.from_numpy(R.seeded_frames(n, 224, 224, 50 + n)).cuda()
+        a, b, c = base.extract_u8(frames, None), alt.extract_u8(frames, None), again.extract_u8(frames, None)
+        assert torch.equal(a, c)
+        if exact:
+            assert torch.equal(a, b), (switch, n)
+        else:
+            err, cos = frame_errors(b.cpu().numpy(), a.cpu().numpy())
+            assert err.max() < 5e-3 and cos.min() > 0.99999, (switch, n, err.max())
+    for e in (base, alt, again):
+        e.close()
+
+
+def test_small_batches_are_bit_identical_to_their_rows_in_a_big_batch(backbone):
+    """Launches with few tiles use narrower N tiles (api.cu: geometry): a frame's features must not depend on it."""
+    e = phdfx.B200Backbone(backbone, device=0, max_frames=64)
+    frames = torch.from_numpy(R.seeded_frames(64, 224, 224, 77)).cuda()
+    big = e.extract_u8(frames, None)
+    for n, at in ((1, 0), (1, 63), (2, 10), (5, 31), (16, 40)):
+        assert torch.equal(e.extract_u8(frames[at:at + n].contiguous(), None), big[at:at + n]), (n, at)
+    e.close()

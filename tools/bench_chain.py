@@ -9,12 +9,11 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200"))
-sys.path.insert(0, str(ROOT / "oracle"))
 
 import torch  # noqa: E402
 
 import phdfx  # noqa: E402
-import resnet50_ref as R  # noqa: E402
+from phdfx import synthetic as R  # noqa: E402
 
 
 def timed(fn, flush, reps):

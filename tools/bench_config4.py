@@ -1,6 +1,6 @@
-"""BASELINE config 4: 200 000 frames (224x224 uint8, generated per rank on the device, seed 4 + rank), contiguous frame
-ranges over the ranks, batch 256, final NCCL gather of the (200000, 2048) fp32 features to rank 0.  Time = max over
-ranks of (extraction of the rank's range + the gather), CUDA events; rank 0 prints one JSON line.
+"""BASELINE config 4 on its own: 200 000 frames (224x224 uint8, generated per rank on the device, seed 4 + rank),
+contiguous frame ranges over the ranks, batch 256, final NCCL gather of the (200000, 2048) fp32 features to rank 0.
+The leg itself lives in bench.py (config4_leg), which also runs it under torchrun; this wrapper runs it alone.
 
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/bench_config4.py [frames]
     python tools/bench_config4.py [frames]          # one GPU, no gather
@@ -11,21 +11,18 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200"))
-sys.path.insert(0, str(ROOT / "oracle"))
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
+import bench  # noqa: E402
 import phdfx  # noqa: E402
-import resnet50_ref as R  # noqa: E402
-from phdfx.dist import shard_range  # noqa: E402
-
-BATCH = 256
 
 
 def main():
-    total = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
+    total = int(sys.argv[1]) if len(sys.argv) > 1 else bench.CONFIG4_FRAMES
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -33,69 +30,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if total % world:
-        raise SystemExit("frames must divide by the world size (equal ranges keep the gather a plain dist.gather)")
-    lo, hi = shard_range(total, rank, world)
-    n = hi - lo
-    eng = phdfx.B200Backbone(R.seeded_backbone(), device=local, max_frames=BATCH)
-    g = torch.Generator(device=dev).manual_seed(4 + rank)
-    frames = torch.empty(n, 224, 224, 3, dtype=torch.uint8, device=dev)  # 150.5 KB per frame: 15 GB at 100k frames
-    for c0 in range(0, n, 2048):
-        c1 = min(n, c0 + 2048)
-        frames[c0:c1] = torch.randint(0, 256, (c1 - c0, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
-    feats = torch.empty(n, 2048, dtype=torch.float32, device=dev)
-    dst = torch.empty(total, 2048, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
-
-    def gather():
-        if world > 1:
-            dist.gather(feats, list(dst.chunk(world)) if rank == 0 else None, dst=0)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for i in range(3):  # warm-up batches + the first (connection-building) collective
-        eng.extract_u8(frames[i * BATCH:(i + 1) * BATCH], None, out=feats[i * BATCH:(i + 1) * BATCH])
-    gather()
-    barrier()
-    # full batches: one CUDA graph over a fixed input slot (D2D copy in, 38.5 MB) and a fixed output slot; the ragged
-    # last batch goes through eager launches
-    slot = torch.empty(BATCH, 224, 224, 3, dtype=torch.uint8, device=dev)
-    out_slot = torch.empty(BATCH, 2048, dtype=torch.float32, device=dev)
-    slot.copy_(frames[:BATCH])
-    graph = eng.capture_extract(slot, None, out=out_slot)
-    graph.replay()
-    barrier()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    launches = 0
-    e0.record()
-    for b0 in range(0, n, BATCH):
-        b1 = min(n, b0 + BATCH)
-        if b1 - b0 == BATCH:
-            slot.copy_(frames[b0:b1])
-            graph.replay()
-            feats[b0:b1].copy_(out_slot)
-            launches += graph.launches
-        else:
-            eng.extract_u8(frames[b0:b1], None, out=feats[b0:b1])
-            launches += eng.launches
-    e1.record()
-    gather()
-    e2.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e2), e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_compute, ms_gather = (float(v) for v in t.tolist())
+    eng = phdfx.B200Backbone(phdfx.seeded_backbone(), device=local, max_frames=bench.BATCH)
+    res = bench.config4_leg(eng, dev, rank, world, total)
     if rank == 0:
-        ok = bool(torch.isfinite(dst if dst is not None else feats).all().item())
-        print(json.dumps({
-            "config": "BASELINE config 4", "frames": total, "n_gpus": world, "batch": BATCH,
-            "frames_per_s": total / (ms_total / 1e3), "ms_total_max_over_ranks": ms_total,
-            "ms_extract_max_over_ranks": ms_compute, "ms_gather_max_over_ranks": ms_gather,
-            "gather_bytes": (total - n) * 2048 * 4 if world > 1 else 0, "gpu_launches_rank0": launches,
-            "launch": "one CUDA-graph replay per full batch of 256 (fixed input slot, D2D copy in), eager for the ragged tail", "finite": ok}))
+        print(json.dumps(res))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -11,12 +11,11 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200"))
-sys.path.insert(0, str(ROOT / "oracle"))
 
 import torch  # noqa: E402
 
 import phdfx  # noqa: E402
-import resnet50_ref as R  # noqa: E402
+from phdfx import synthetic as R  # noqa: E402
 
 FLOP_PER_FRAME = 2 * 4_087_136_256
 BATCHES = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024]

@@ -9,8 +9,9 @@ Measured on the v8 build (B200, batch 256, L2 flushed): layer3.1.conv3 0.051 / 0
 not 2x: at 148 SMs both are partly limited by what the SMs share (aggregate L2 -> SM operand bandwidth).
 """
 import os, sys, json
-sys.path.insert(0, "implementation-phd-lab-vision_b200"); sys.path.insert(0, "oracle")
-import torch, phdfx, resnet50_ref as R
+sys.path.insert(0, "implementation-phd-lab-vision_b200")
+import torch, phdfx
+from phdfx import synthetic as R
 cap = os.environ.get("PHDFX_SM_CAP", "148")
 n = 256
 eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)

@@ -2,8 +2,8 @@
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200")); sys.path.insert(0, str(ROOT / "oracle"))
-import torch, phdfx, resnet50_ref as R
+sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200")); import torch, phdfx
+from phdfx import synthetic as R
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
 frames = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device="cuda")

@@ -10,6 +10,10 @@
 import csv
 import json
 import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "implementation-phd-lab-vision_b200"))
+from phdfx.synthetic import csrc_sha  # noqa: E402  (content hash of the kernel sources the capture was taken with)
 
 COLS = ["ID", "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -47,6 +51,7 @@ def main():
         name = d[idx["Kernel Name"]].split("(")[0].replace("void ", "")
         per_kernel[name] = per_kernel.get(name, 0.0) + t
     json.dump({"source": f"ncu --set full, one step at batch 256 ({len(data)} trunk launches), {out_csv}",
+               "csrc_sha": csrc_sha(),
                "launches": len(data), "dram_bytes_read": rd, "dram_bytes_write": wr,
                "traffic_bytes_per_step": rd + wr, "sum_kernel_us": sum(us),
                "time_weighted_tensor_pipe_pct": sum(a * b for a, b in zip(us, tc)) / sum(us),

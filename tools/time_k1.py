@@ -2,8 +2,8 @@
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200")); sys.path.insert(0, str(ROOT / "oracle"))
-import torch, phdfx, resnet50_ref as R
+sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200")); import torch, phdfx
+from phdfx import synthetic as R
 n = 256
 eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
 jit = torch.stack([phdfx.jitter_params([2, 0, 3, 1], 1.2, 0.9, 1.1, 0.02)] * n).cuda()

@@ -2,8 +2,8 @@
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200")); sys.path.insert(0, str(ROOT / "oracle"))
-import torch, phdfx, resnet50_ref as R
+sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200")); import torch, phdfx
+from phdfx import synthetic as R
 i = int(sys.argv[1]); n = int(sys.argv[2]) if len(sys.argv) > 2 else 256; reps = int(sys.argv[3]) if len(sys.argv) > 3 else 7
 eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
 L = eng.plan.layers[i]

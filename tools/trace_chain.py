@@ -8,7 +8,6 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200"))
-sys.path.insert(0, str(ROOT / "oracle"))
 raw = str(ROOT / "gpurun_out" / "chain_trace_raw.txt")
 if os.path.exists(raw):
     os.remove(raw)
@@ -17,7 +16,7 @@ os.environ["PHDFX_CHAIN_TRACE"] = raw
 import torch  # noqa: E402
 
 import phdfx  # noqa: E402
-import resnet50_ref as R  # noqa: E402
+from phdfx import synthetic as R  # noqa: E402
 
 EV = {0: "mma conv2 start", 1: "mma conv2 issued", 2: "mma conv3 issue", 3: "mma conv1n start", 4: "mma conv1n issued",
       5: "epi A start", 6: "epi A end", 7: "epi B start", 8: "epi B g0", 9: "epi B g1", 10: "epi B g2", 11: "epi B g3",

@@ -8,13 +8,12 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "implementation-phd-lab-vision_b200"))
-sys.path.insert(0, str(ROOT / "oracle"))
 raw = str(ROOT / "gpurun_out" / "conv_trace_raw.txt")
 
 import torch  # noqa: E402
 
 import phdfx  # noqa: E402
-import resnet50_ref as R  # noqa: E402
+from phdfx import synthetic as R  # noqa: E402
 
 EV = {0: "tma first load", 1: "tma last load", 2: "mma tile start", 3: "mma acc free", 4: "mma issued", 8: "dma res g0",
       9: "dma res g1", 10: "dma res g2", 11: "dma res g3", 12: "dma st g0", 13: "dma st g1", 14: "dma st g2",
