@@ -138,6 +138,17 @@ def real_dataset(args):
 
         tvio.VideoReader = _no_video_reader
     try:
+        explicit = os.path.join(args.dataset_path, "dataset.py") if args.dataset_path else None
+        if explicit and os.path.isfile(explicit):
+            # --dataset-path names THE file to use: load it even when some other `dataset` module is already imported
+            # in this process (an embedding application, a test session), and register it under the name its classes
+            # pickle by
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("dataset", explicit)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["dataset"] = mod
+            spec.loader.exec_module(mod)
         from dataset import Human36MPreprocessedClips  # the user's / reference's dataset.py
     except Exception as e:  # noqa: BLE001
         raise RuntimeError(
