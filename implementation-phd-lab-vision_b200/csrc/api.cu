@@ -93,6 +93,12 @@ struct phdfx {
   bool use_rev = true;              // PHDFX_NO_REV=1: every launch walks its tiles in ascending order
   bool use_halo = true;             // PHDFX_NO_HALO=1: 3x3/1 convs of layer1 / layer2 through the im2col path
   bool use_small_n = true;          // PHDFX_NO_SMALL_N=1: keep 256-wide N tiles for launches with few tiles
+  bool use_flags = false;           // PHDFX_FLAGS=1: launches follow their predecessor's frame progress counters
+  size_t flag_max_bytes = 64u << 20;  // PHDFX_FLAG_MAX_MB: larger tensors keep griddepcontrol.wait + serpentine order
+  int real_sms = 0;                 // SMs of the device (num_sms may be capped for experiments)
+  uint32_t* d_ctrs = nullptr;       // frame progress counters, [n_layers][max_frames + 1] (conv_igemm_sm100.cuh)
+  std::string cta_trace_path;       // PHDFX_CTA_TRACE=file: per-CTA %globaltimer stamps of every conv launch of a pass
+  unsigned long long* d_cta_ts = nullptr;  // [n_layers][kTraceCtas][6]
   std::vector<int> chain_span;      // per layer: layers covered by the fused launch STARTING there (0 = none)
   std::vector<Stage> stages;        // execution schedule (default: one stage, no waves)
   int sched_flags = 0;
@@ -432,8 +438,18 @@ int launch_conv_cg2_t(phdfx_t* h, const LayerMaps& maps, const ConvParams& p, cu
   return 0;
 }
 
+// how a launch is tied to its neighbours in the stream (frame progress counters, conv_igemm_sm100.cuh)
+constexpr int kTraceCtas = 256;
+struct LaunchDep {
+  unsigned long long* cta_ts = nullptr;  // debug timeline of this launch's CTAs
+  const uint32_t* wait = nullptr;  // predecessor's counters; nullptr = griddepcontrol.wait
+  uint32_t full = 0;
+  uint32_t ctas = 0;               // CTAs of the predecessor's grid
+  uint32_t* sig = nullptr;
+};
+
 int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, const void* res, void* out, int n,
-                cudaStream_t st, int rev = 0, long long* trace = nullptr) {
+                cudaStream_t st, int rev = 0, long long* trace = nullptr, const LaunchDep& dep = LaunchDep()) {
   const bool has_res = res != nullptr;
   const Geo g = geometry(h, L, n);
   ConvParams p{};
@@ -457,6 +473,12 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, co
   p.src2_stride = L.in2_buf >= 0 ? L.stride2 : 1;
   p.rev = rev;
   p.trace = trace;
+  p.cta_ts = dep.cta_ts;
+  p.wait_ctr = dep.wait;
+  p.wait_full = dep.full;
+  p.wait_ctas = dep.ctas;
+  p.ctr_frames = h->max_frames;
+  p.sig_ctr = dep.sig;
   if (g.mode == MODE_HALO)
     p.m_tiles = n * (g.P / g.halo_rt);
   else if (g.mode == MODE_STEM)
@@ -609,7 +631,7 @@ int build_stem_pool_map(phdfx_t* h, void* out, int frames, CUtensorMap* m) {
 }
 
 int launch_stem_pool(phdfx_t* h, const phdfx_layer_desc& L, const CUtensorMap& map_out, const void* in, int n,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool zero_ctrs = false) {
   static bool attr_set[64] = {};
   const int smem = StemPoolSmem::TOTAL + 1024;
   if (!attr_set[h->device & 63]) {
@@ -621,6 +643,10 @@ int launch_stem_pool(phdfx_t* h, const phdfx_layer_desc& L, const CUtensorMap& m
   p.weights = h->d_weights + L.w_off;
   p.bias = h->d_bias + L.b_off;
   p.n_frames = n;
+  if (zero_ctrs) {  // the first launch of a pass resets the frame progress counters of the launches behind it
+    p.zero_ptr = h->d_ctrs;
+    p.zero_words = static_cast<int>(h->layers.size()) * (h->max_frames + 1);
+  }
   const int bands = n * kSpBandsPerFrame;
   const int grid = bands < h->num_sms ? bands : h->num_sms;
   CUDA_TRY(h, launch_pdl(stem_pool_kernel, dim3(grid), dim3(kSpThreads), smem, st, map_out, p));
@@ -656,6 +682,10 @@ void free_device_state(phdfx_t* h) {
   if (h->d_weights) cudaFree(h->d_weights);
   if (h->d_bias) cudaFree(h->d_bias);
   if (h->d_row_sums) cudaFree(h->d_row_sums);
+  if (h->d_ctrs) cudaFree(h->d_ctrs);
+  if (h->d_cta_ts) cudaFree(h->d_cta_ts);
+  h->d_cta_ts = nullptr;
+  h->d_ctrs = nullptr;
   h->d_row_sums = nullptr;
   h->d_weights = nullptr;
   h->d_bias = nullptr;
@@ -713,7 +743,8 @@ int k1_launch(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const in
 // wave-local region), fetches / builds the tensor maps for exactly those pointers and that frame count, and launches
 // (dry = build the maps only).  *span = execution-list entries covered (a fused chain covers 2 or 3).
 int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, const void* ext_in, bool buf0_local,
-               float* d_feats, cudaStream_t st, int rev, bool dry, int* span) {
+               float* d_feats, cudaStream_t st, int rev, bool dry, int* span, const LaunchDep& dep = LaunchDep(),
+               bool zero_ctrs = false) {
   const auto& L = h->layers[i];
   // frame f of a tensor lives at base + f * (the TENSOR's bytes per frame) — the dense layout an un-waved pass uses, so
   // a stage may read what a differently-waved stage wrote; wave-local tensors sit at frame 0 (+ slot) of their buffer
@@ -791,9 +822,52 @@ int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, cons
     maps = &cache.back().maps;
   }
   if (dry) return 0;
-  if (L.kind == PHDFX_STEM_POOL) return launch_stem_pool(h, L, maps->o, at(L.in_buf, in_bpf(L)), m, st);
+  if (L.kind == PHDFX_STEM_POOL) return launch_stem_pool(h, L, maps->o, at(L.in_buf, in_bpf(L)), m, st, zero_ctrs);
   void* out = L.gap ? static_cast<void*>(d_feats + static_cast<size_t>(f0) * L.cout) : const_cast<void*>(k.out);
-  return launch_conv(h, L, *maps, k.res, out, m, st, rev);
+  return launch_conv(h, L, *maps, k.res, out, m, st, rev, nullptr, dep);
+}
+
+// Which launches of an un-waved pass over n frames start on their predecessor's frame progress counters instead of
+// griddepcontrol.wait (conv_igemm_sm100.cuh, "Frame progress counters").  link[i] = 1: the launch at execution-list
+// entry i waits on the counters of the launch in front of it.  The conditions are what makes the scheme safe:
+//  * both launches are plain conv launches on full grids (one CTA on every SM of the device), so at most two
+//    consecutive launches are ever resident together and everything older than the predecessor has completed;
+//  * the successor's A operand is the predecessor's output and nothing else of the predecessor's is read by it;
+//  * the successor does not write a buffer the predecessor still reads;
+//  * the first launch of the pass is the fused stem, which zeroes the counters behind a full grid dependency.
+// Large tensors keep the serpentine order (the successor starts on the rows written last, while they are in L2),
+// which needs the whole predecessor grid to be done anyway.
+std::vector<char> plan_links(const phdfx_t* h, int n) {
+  const int nl = static_cast<int>(h->layers.size());
+  std::vector<char> link(nl, 0);
+  if (!h->use_flags || !h->d_ctrs || h->num_sms != h->real_sms || h->stages.size() != 1 || h->stages[0].wave != 0 ||
+      h->layers[0].kind != PHDFX_STEM_POOL)
+    return link;
+  auto full_grid = [&](const phdfx_layer_desc& L, const Geo& g) {
+    const long long m_tiles = g.mode == MODE_GAP ? (n + 1) / 2 : (static_cast<long long>(n) * g.P * g.Q + kBlockM - 1) / kBlockM;
+    const long long n_tiles = L.cout / g.bn;
+    return g.cg2 ? ((m_tiles + 1) / 2) * n_tiles >= h->num_sms / 2 : m_tiles * n_tiles >= h->num_sms;
+  };
+  int prev = -1;
+  for (int i = 0; i < nl;) {
+    const int span = h->chain_span[i] > 0 ? h->chain_span[i] : 1;
+    if (prev >= 0 && span == 1 && h->chain_span[prev] == 0) {
+      const auto& A = h->layers[prev];
+      const auto& B = h->layers[i];
+      if (A.kind == PHDFX_CONV && B.kind == PHDFX_CONV && !A.gap) {
+        const Geo ga = geometry(h, A, n), gb = geometry(h, B, n);
+        const bool modes = (ga.mode == MODE_TILED || ga.mode == MODE_IM2COL) &&
+                           (gb.mode == MODE_TILED || gb.mode == MODE_IM2COL || gb.mode == MODE_GAP);
+        const bool reads = B.in_buf == A.out_buf && B.res_buf != A.out_buf && B.in2_buf != A.out_buf;
+        const bool war = !B.gap && (B.out_buf == A.in_buf || B.out_buf == A.in2_buf || B.out_buf == A.res_buf);
+        const size_t bytes = static_cast<size_t>(n) * out_elems_per_frame(A) * 2;
+        if (modes && reads && !war && full_grid(A, ga) && full_grid(B, gb) && bytes <= h->flag_max_bytes) link[i] = 1;
+      }
+    }
+    prev = i;
+    i += span;
+  }
+  return link;
 }
 
 // what feeds arena buffer 0 (the NHWC4p network input) during a pass over the schedule
@@ -840,6 +914,10 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   if (const char* e = getenv("PHDFX_NO_CG2")) h->use_cg2 = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_REV")) h->use_rev = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_SMALL_N")) h->use_small_n = !(e[0] == '1');
+  if (const char* e = getenv("PHDFX_FLAGS")) h->use_flags = e[0] == '1';
+  if (const char* e = getenv("PHDFX_FLAG_MAX_MB")) h->flag_max_bytes = static_cast<size_t>(atoi(e)) << 20;
+  h->real_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("PHDFX_CTA_TRACE")) h->cta_trace_path = e;
   if (const char* e = getenv("PHDFX_SM_CAP")) {  // experiments: run every persistent grid on fewer SMs
     const int cap = atoi(e);
     if (cap >= 2 && cap < h->num_sms) h->num_sms = cap & ~1;
@@ -913,6 +991,12 @@ int phdfx_load_weights(phdfx_t* h, const void* packed_bf16, int64_t n_weights, c
     CUDA_TRY(h, cudaMemset(h->bufs[i], 0, h->buf_bytes[i] * h->max_frames + kArenaSlack));
   }
   CUDA_TRY(h, cudaMalloc(&h->d_row_sums, static_cast<size_t>(h->max_frames) * kImg * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d_ctrs, static_cast<size_t>(n_layers) * (h->max_frames + 1) * sizeof(uint32_t)));
+  CUDA_TRY(h, cudaMemset(h->d_ctrs, 0, static_cast<size_t>(n_layers) * (h->max_frames + 1) * sizeof(uint32_t)));
+  if (!h->cta_trace_path.empty()) {
+    CUDA_TRY(h, cudaMalloc(&h->d_cta_ts, static_cast<size_t>(n_layers) * kTraceCtas * 6 * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemset(h->d_cta_ts, 0, static_cast<size_t>(n_layers) * kTraceCtas * 6 * sizeof(unsigned long long)));
+  }
   for (int i = 0; i < n_layers; ++i) {
     const auto& L = h->layers[i];
     if (!h->bufs[L.in_buf]) return fail(h, PHDFX_ERR_INVALID, "layer %d reads buffer %d that no layer writes", i, L.in_buf);
@@ -1014,6 +1098,10 @@ static int forward_impl(phdfx_t* h, const Source& src, int n, float* d_feats, cu
       ends[s].push_back(acc);
     }
   }
+  const std::vector<char> link = plan_links(h, n);
+  bool any_link = false;
+  for (char c : link) any_link |= c != 0;
+  int prev_rev = 1;
   std::vector<int> done(S, 0), idx(S, 0);
   const bool buf0_local = (h->sched_flags & PHDFX_SCHED_REUSE) && src.frames != nullptr && h->stages[0].wave > 0;
   bool wrote_feats = false;
@@ -1033,11 +1121,27 @@ static int forward_impl(phdfx_t* h, const Source& src, int n, float* d_feats, cu
         return rc;
     }
     for (int i = sg.first; i < sg.last; ++launch_no) {
-      // serpentine: odd launches walk their tiles backwards, i.e. start where the previous launch ended
-      const int rev = (h->use_rev && (launch_no & 1)) ? 1 : 0;
+      // serpentine: a launch walks its tiles in the opposite direction of its predecessor, i.e. starts where that one
+      // ended — unless it follows the predecessor's frame progress counters, then in the same direction
+      const int rev = h->use_rev ? (link[i] ? prev_rev : 1 - prev_rev) : 0;
+      prev_rev = rev;
       int span = 1;
       mark(i);
-      if (int rc = run_launch(h, sg, i, f0, m, 0, src.d_in, buf0_local, d_feats, st, rev, false, &span)) return rc;
+      LaunchDep dep;
+      if (link[i]) {
+        int a = i - 1;  // the launch in front (links only exist between single-entry launches)
+        const auto& A = h->layers[a];
+        const Geo ga = geometry(h, A, m);
+        dep.wait = h->d_ctrs + static_cast<size_t>(a) * (h->max_frames + 1);
+        dep.full = static_cast<uint32_t>(ga.P * ga.Q) * static_cast<uint32_t>(A.cout / 64);
+        dep.ctas = static_cast<uint32_t>(h->num_sms);  // links only exist between full grids
+      }
+      if (i + 1 < static_cast<int>(link.size()) && link[i + 1] && h->chain_span[i] == 0)
+        dep.sig = h->d_ctrs + static_cast<size_t>(i) * (h->max_frames + 1);
+      if (h->d_cta_ts) dep.cta_ts = h->d_cta_ts + static_cast<size_t>(i) * kTraceCtas * 6;
+      if (int rc = run_launch(h, sg, i, f0, m, 0, src.d_in, buf0_local, d_feats, st, rev, false, &span, dep,
+                              any_link && i == 0))
+        return rc;
       for (int j = i; j < i + span; ++j)
         if (h->layers[j].gap) wrote_feats = true;
       i += span;
@@ -1047,6 +1151,27 @@ static int forward_impl(phdfx_t* h, const Source& src, int n, float* d_feats, cu
   }
   mark(-2);
   if (!wrote_feats) return fail(h, PHDFX_ERR_STATE, "layer list has no gap layer: nothing wrote d_feats");
+  if (h->d_cta_ts) {
+    // debug: dump the CTA timeline of this pass (synchronises; not usable under stream capture)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      CUDA_TRY(h, cudaStreamSynchronize(st));
+      const size_t nl = h->layers.size();
+      std::vector<unsigned long long> host(nl * kTraceCtas * 6);
+      CUDA_TRY(h, cudaMemcpy(host.data(), h->d_cta_ts, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(h->cta_trace_path.c_str(), "w")) {
+        for (size_t l = 0; l < nl; ++l)
+          for (int c = 0; c < kTraceCtas; ++c) {
+            const unsigned long long* r = &host[(l * kTraceCtas + c) * 6];
+            if (r[0] | r[2])
+              fprintf(f, "%zu %d %llu %llu %llu %llu %d %llu\n", l, c, r[0], r[1], r[2], r[3], link[l] ? 1 : 0, r[4]);
+          }
+        fclose(f);
+      }
+      CUDA_TRY(h, cudaMemset(h->d_cta_ts, 0, host.size() * sizeof(unsigned long long)));
+    }
+  }
   return 0;
 }
 
@@ -1306,6 +1431,13 @@ int phdfx_run_chain(phdfx_t* h, int first_layer_id, const void* d_t1, const void
     return rc;
   }
   return launch_chain(h, cp, n, static_cast<cudaStream_t>(stream), 0);
+}
+
+int phdfx_linked_launches(const phdfx_t* h, int n) {
+  if (!h || h->layers.empty() || n < 1 || n > h->max_frames) return 0;
+  int c = 0;
+  for (char l : plan_links(h, n)) c += l != 0;
+  return c;
 }
 
 int phdfx_layer_count(const phdfx_t* h) { return h ? static_cast<int>(h->layers.size()) : 0; }

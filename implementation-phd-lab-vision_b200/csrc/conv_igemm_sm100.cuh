@@ -58,6 +58,18 @@ struct ConvParams {
                    // on the rows its predecessor wrote last — the part of the activation tensor still resident in L2
   const float* bias;  // [Cout] folded BN bias
   float* feats;       // MODE_GAP: [n_frames, Cout]
+  // Frame progress counters (see dep_wait_frames): wait_ctr != nullptr replaces griddepcontrol.wait — the launch starts
+  // a tile as soon as the launch that produces its A operand has published the tile's frames; sig_ctr != nullptr makes
+  // this launch publish its own output the same way.  Both index by frame of the call.
+  unsigned long long* cta_ts;  // debug (PHDFX_CTA_TRACE): 6 words per CTA: %globaltimer at [4] entry, [0] prologue done, [1] first tile's
+                               // inputs available, [2] exit; [3] = ns the TMA producer warp spent waiting on counters
+  const uint32_t* wait_ctr;
+  uint32_t wait_full;  // counter value of a complete input frame: (producer's output rows per frame) x (its Cout / 64)
+  uint32_t* sig_ctr;
+  // [n_frames] of either array counts CTAs of the producing grid that have published everything (wait_ctas = that
+  // grid's size): once a consumer CTA has seen it complete it stops polling — a poll is an L2 round trip per tile
+  int ctr_frames;
+  uint32_t wait_ctas;
   long long* trace;   // debug (PHDFX_CONV_TRACE): CTA 0 writes clock64() of pipeline events, [tile < 32][32 events]
 };
 
@@ -70,6 +82,64 @@ constexpr int kGapRows = 98;
 constexpr int kStemTileQ = 16, kStemTileP = 8, kStemOut = 112, kStemTilesPerFrame = (112 / 16) * (112 / 8);
 constexpr int kGroupCols = 64;                        // channels per epilogue group (= one 128 B swizzle row)
 constexpr int kStageOutBytes = kBlockM * 128;         // one staging buffer: 128 rows x 128 B
+
+// ---- Frame progress counters: tile-granular dependencies between ADJACENT launches -------------------------------
+// Every kernel of the library is a persistent grid of one CTA per SM that triggers its dependents (PDL) at start, so the
+// next launch's CTAs take over SMs as this launch's CTAs exit.  With griddepcontrol.wait they then sit idle until the
+// WHOLE grid has drained — up to a full tile time when the tile count is not a multiple of the grid (layer4: 98
+// pair-tiles on 74 CTA pairs).  Instead, a producer launch adds (rows x 64-channel groups) to a per-frame counter once
+// the TMA stores of a tile have completed, and the consumer's TMA producer warp polls the counters of the frames a tile
+// reads before its first load.  Frames are the unit because every consumer on this path needs whole frames (3x3) or a
+// row range inside one or two frames (1x1).  Only the predecessor's output is guarded this way; what a launch reads from
+// further back (residual, down-sample source) was complete before this launch could start: a grid of num_sms CTAs with
+// one CTA per SM is fully resident only after every CTA of the grid before it has exited, and the dependent launch
+// starts only after every CTA of this grid has started.  The host links two launches only under those conditions
+// (api.cu: plan_links) and zeroes the counters at the start of every pass.
+// Whole converged warp: lane i owns frame f_lo + i of the tile (a tile touches at most a few frames).
+__device__ __forceinline__ void dep_wait_frames(const uint32_t* ctr, uint32_t full, int f_lo, int f_hi) {
+  const int f = f_lo + static_cast<int>(threadIdx.x & 31);
+  if (f <= f_hi) {
+    uint32_t v = 0u;
+#ifdef PHDFX_TRAP
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+#endif
+    while (v < full) {
+      v = ld_acquire_gpu(ctr + f);
+#ifdef PHDFX_TRAP
+      if ((++spins & 0x3FFu) == 0) {
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0)
+          t0 = now;
+        else if (now - t0 > kMbarTrapNs)
+          __trap();
+      }
+#endif
+    }
+  }
+  __syncwarp();
+  fence_proxy_async_all();  // the TMA loads that follow (async proxy) observe what the acquire made visible
+}
+// whole converged warp: has every CTA of the producing grid published all its tiles?
+__device__ __forceinline__ bool dep_grid_done(const uint32_t* done_ctr, uint32_t grid_ctas) {
+  const bool done = ld_acquire_gpu(done_ctr) >= grid_ctas;
+  if (done) fence_proxy_async_all();
+  return done;
+}
+// one thread, after the TMA stores of output rows [r0, r1) have COMPLETED (wait_group without .read): `per_row` = the
+// 64-channel groups of the tile
+__device__ __forceinline__ void dep_signal_rows(uint32_t* ctr, int r0, int r1, int pq, uint32_t per_row) {
+  fence_proxy_async_all();
+  int f = r0 / pq;
+  int f_end = (f + 1) * pq;
+  while (r0 < r1) {
+    const int e = r1 < f_end ? r1 : f_end;
+    red_release_gpu_add(ctr + f, static_cast<uint32_t>(e - r0) * per_row);
+    r0 = e;
+    ++f;
+    f_end += pq;
+  }
+}
 
 template <int BN, int MODE>
 struct ConvCfg {
@@ -137,6 +207,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
+  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 4] = global_timer_ns();  // kernel entry
   const int num_tiles = p.m_tiles * p.n_tiles;
   // debug timeline: event e of this CTA's k-th tile (CTA 0 only, first 32 tiles)
   auto mark = [&](int k, int e) {
@@ -182,7 +253,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's
   // tail; nothing below touches activations before the previous grid has completed.
   griddep_launch_dependents();
-  griddep_wait();
+  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 0] = global_timer_ns();
+  if (p.wait_ctr == nullptr) griddep_wait();
+  if (p.cta_ts != nullptr && threadIdx.x == 0 && p.wait_ctr == nullptr) p.cta_ts[blockIdx.x * 6 + 1] = global_timer_ns();
+  unsigned long long dep_ns = 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -196,6 +270,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           tma_load_2d_elect(&mapB, &full_bar[tap], smem + tap * Cfg::STAGE_BYTES, tap * 64, 0);
         }
       }
+      bool dep_all = false;  // frame progress counters: the producing grid is known to have published everything
+      auto frames_of = [&](int mb, int* f_lo, int* f_hi) {
+        if (MODE == MODE_GAP) {
+          *f_lo = mb * 2;
+          *f_hi = mb * 2 + 1 < p.n_frames ? mb * 2 + 1 : p.n_frames - 1;
+        } else {
+          const int pq = p.P * p.Q;
+          const int r1 = (mb + 1) * kBlockM < p.M ? (mb + 1) * kBlockM : p.M;
+          *f_lo = (mb * kBlockM) / pq;
+          *f_hi = (r1 - 1) / pq;
+        }
+      };
       for (int lt = blockIdx.x; lt < num_tiles; lt += gridDim.x) {
         const int tile = p.rev ? num_tiles - 1 - lt : lt;
         const int m_blk = tile / p.n_tiles;
@@ -227,6 +313,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const int tpf = p.P / p.halo_rt;  // tiles per frame
           cn = m_blk / tpf;
           ch = (m_blk - cn * tpf) * p.halo_rt - 1;  // first input row of the patch (-1 = zero halo)
+        }
+        if (p.wait_ctr != nullptr) {
+          // frames this tile reads from the previous launch (= the frames of its output rows); then read ahead for
+          // the next tile of this CTA
+          int f_lo, f_hi;
+          const unsigned long long tw = p.cta_ts != nullptr ? global_timer_ns() : 0ull;
+          if (!dep_all) dep_all = dep_grid_done(p.wait_ctr + p.ctr_frames, p.wait_ctas);
+          if (!dep_all) {
+            frames_of(m_blk, &f_lo, &f_hi);
+            dep_wait_frames(p.wait_ctr, p.wait_full, f_lo, f_hi);
+          }
+          if (p.cta_ts != nullptr) {
+            const unsigned long long now = global_timer_ns();
+            dep_ns += now - tw;
+            if (lt == static_cast<int>(blockIdx.x) && lane == 0) p.cta_ts[blockIdx.x * 6 + 1] = now;
+          }
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           if (kb == 0) mark((lt - blockIdx.x) / gridDim.x, 0);
@@ -374,6 +476,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                                      static_cast<int>(gridDim.x)
                                : 0;
       const int J = my_tiles * GROUPS;
+      constexpr int kSigLag = 2;
+      const bool sig_now = p.num_kb >= 16;
+      // publish this CTA's ti-th tile (its stores have completed): rows x GROUPS per frame
+      auto signal_tile = [&](int ti) {
+        const int lt = blockIdx.x + ti * gridDim.x;
+        const int tile = p.rev ? num_tiles - 1 - lt : lt;
+        const int m_blk = tile / p.n_tiles;
+        const int r1 = (m_blk + 1) * kBlockM < p.M ? (m_blk + 1) * kBlockM : p.M;
+        dep_signal_rows(p.sig_ctr, m_blk * kBlockM, r1, p.P * p.Q, GROUPS);
+      };
       for (int t = 0; t < J + LOOK; ++t) {
         if (t < J) {
           // A(t): make buffer t % NB available to the epilogue warps (with the residual tile in it, if any)
@@ -420,10 +532,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
             tma_store_commit();
             if (g < 4) mark(u / GROUPS, 12 + g);
+            if ((MODE == MODE_TILED || MODE == MODE_IM2COL) && p.sig_ctr != nullptr) {
+              // Publish a tile once its stores have been WRITTEN (wait_group without .read).  MMA-bound launches (long K)
+              // emit a tile's groups in a burst and then nothing for a long time: wait right away, this thread has nothing
+              // else to do.  Epilogue-bound launches emit groups continuously: publish kSigLag groups late, when the wait
+              // returns at once, so the residual loads this thread issues for the groups ahead are not held up.
+              if (sig_now) {
+                if (g == GROUPS - 1) {
+                  tma_store_wait_all<0>();
+                  signal_tile(u / GROUPS);
+                }
+              } else if (u >= kSigLag && (u - kSigLag) % GROUPS == GROUPS - 1) {
+                tma_store_wait_all<kSigLag>();
+                signal_tile((u - kSigLag) / GROUPS);
+              }
+            }
           }
         }
       }
-      if (MODE != MODE_GAP) tma_store_wait_all<0>();
+      // a CTA may exit once its stores have been READ out of shared memory: the writes complete with the grid, which is
+      // what the next launch waits for; only a launch that publishes progress itself has to see them written first
+      if (MODE != MODE_GAP) {
+        if (p.sig_ctr != nullptr)
+          tma_store_wait_all<0>();
+        else
+          tma_store_wait_read<0>();
+      }
+      if ((MODE == MODE_TILED || MODE == MODE_IM2COL) && p.sig_ctr != nullptr) {
+        if (!sig_now)
+          for (int w = (J > kSigLag ? J - kSigLag : 0); w < J; ++w)
+            if (w % GROUPS == GROUPS - 1) signal_tile(w / GROUPS);
+        red_release_gpu_add(p.sig_ctr + p.ctr_frames, 1u);  // this CTA has published everything
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (warps 4..11)
@@ -558,8 +698,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   }
 
+  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 3] = dep_ns;
   tc_fence_before();
   __syncthreads();
+  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 2] = global_timer_ns();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

@@ -44,13 +44,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // -DPHDFX_TRAP (debug builds, used while developing a kernel) bounds every wait by TIME (%globaltimer, 20 s) and traps,
 // so a pipeline bug (lost arrive, wrong tx count) ends the kernel instead of hanging the GPU; a legitimately long wait
 // (time-sliced GPU, MPS neighbour, profiler replay) never comes near the bound.
-#ifdef PHDFX_TRAP
-constexpr unsigned long long kMbarTrapNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef PHDFX_TRAP
+constexpr unsigned long long kMbarTrapNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
 #endif
 #ifndef PHDFX_SPIN_SLEEP_NS
 #define PHDFX_SPIN_SLEEP_NS 0
@@ -176,6 +176,21 @@ __device__ __forceinline__ void tma_store_wait_all() {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- tile-granular dependencies between launches
+// A launch may start consuming its predecessor's output before the predecessor's grid has completed (conv_igemm_sm100.cuh,
+// "Frame progress counters"): the producer publishes per-frame progress with a release-add AFTER its TMA stores have
+// completed (cp.async.bulk.wait_group without .read) and a proxy fence; the consumer polls with acquire loads and fences
+// the async proxy before its TMA loads of those frames.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM

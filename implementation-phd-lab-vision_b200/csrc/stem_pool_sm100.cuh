@@ -59,6 +59,8 @@ struct StemPoolParams {
   const __nv_bfloat16* weights;  // pre-laid-out smem image, kSpWeightBytes
   const float* bias;             // [64]
   int n_frames;
+  uint32_t* zero_ptr;            // frame progress counters of the pass this launch opens (conv_igemm_sm100.cuh), or
+  int zero_words;                // nullptr: zeroed here, behind this launch's full grid dependency
 };
 
 // executed by a whole converged warp; one elected lane issues (keeps operands in uniform registers)
@@ -141,6 +143,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
   const uint32_t tmem_base = *tmem_ptr;
   griddep_launch_dependents();  // PDL: see conv_igemm_sm100.cuh
   griddep_wait();
+  if (p.zero_ptr != nullptr)
+    for (int i = blockIdx.x * kSpThreads + threadIdx.x; i < p.zero_words; i += gridDim.x * kSpThreads) p.zero_ptr[i] = 0u;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (whole warp, uniform flow)
@@ -263,7 +267,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
           }
         }
       }
-      tma_store_wait_all<0>();
+      tma_store_wait_read<0>();  // the CTA may exit once its stores have left shared memory (conv_igemm_sm100.cuh)
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue + pool (warps 4..11)

@@ -34,6 +34,7 @@ EXPORTS = [
     "phdfx_layer_count",
     "phdfx_layer_info",
     "phdfx_last_launch_count",
+    "phdfx_linked_launches",
 ]
 
 PHDFX_CONV, PHDFX_STEM, PHDFX_MAXPOOL, PHDFX_STEM_POOL = 0, 1, 2, 3
@@ -128,6 +129,8 @@ def load() -> C.CDLL:
     lib.phdfx_layer_count.argtypes = [vp]
     lib.phdfx_layer_info.restype = i32
     lib.phdfx_layer_info.argtypes = [vp, i32, C.POINTER(LayerDesc)]
+    lib.phdfx_linked_launches.restype = i32
+    lib.phdfx_linked_launches.argtypes = [vp, i32]
     lib.phdfx_last_launch_count.restype = i32
     lib.phdfx_last_launch_count.argtypes = [vp]
     _lib = lib

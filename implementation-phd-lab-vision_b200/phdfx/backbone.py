@@ -129,6 +129,10 @@ class B200Backbone:
         if not t.is_contiguous():
             raise RuntimeError(f"{name} must be contiguous")
 
+    def linked_launches(self, n: int) -> int:
+        """Launches of a pass over n frames that follow their predecessor's frame progress counters (include/phdfx.h)."""
+        return int(self._lib.phdfx_linked_launches(self._h, int(n)))
+
     @property
     def last_launch_count(self) -> int:
         return int(self._lib.phdfx_last_launch_count(self._h))

@@ -167,6 +167,16 @@ int phdfx_run_chain(phdfx_t* h, int first_layer_id, const void* d_t1, const void
 int phdfx_set_schedule(phdfx_t* h, const int32_t* first_layer, const int32_t* wave_frames, int n_stages, int flags);
 int phdfx_get_schedule(const phdfx_t* h, int32_t* first_layer, int32_t* wave_frames, int cap, int* flags);
 
+/* Tile-granular dependencies between launches (opt-in: PHDFX_FLAGS=1 in the environment at phdfx_create).  A launch
+ * starts (programmatic dependent launch) while its predecessor drains but touches no activation before that grid has
+ * completed.  With the switch on, where it is safe — two consecutive plain conv launches on full grids, the second
+ * reading only the first's output of at most PHDFX_FLAG_MAX_MB (default 64) MB — phdfx_forward instead lets the second
+ * launch start each tile as soon as the first has published the frames that tile reads (per-frame progress counters,
+ * csrc/conv_igemm_sm100.cuh).  Results are bit-identical.  Measured neutral on B200 (a CTA of the next
+ * launch only becomes resident ~5 us after its predecessor's CTA exits, whatever it waits on afterwards), hence off by
+ * default.  phdfx_linked_launches: how many launches of a pass over n frames start that way. */
+int phdfx_linked_launches(const phdfx_t* h, int n);
+
 int phdfx_layer_count(const phdfx_t* h);
 int phdfx_layer_info(const phdfx_t* h, int layer_id, phdfx_layer_desc* out);
 /* Number of kernels the last phdfx_forward / phdfx_extract_u8 / phdfx_preprocess_u8 call launched. */

@@ -561,6 +561,48 @@ def test_kernel_selection_switches(backbone, switch, exact):
         e.close()
 
 
+@pytest.mark.parametrize("n", [100, 200, 256])
+def test_frame_progress_links_are_bit_identical(backbone, n):
+    """Launches that start on their predecessor's per-frame progress counters instead of waiting for its whole grid
+    (include/phdfx.h: phdfx_linked_launches; csrc/conv_igemm_sm100.cuh) read the same bytes in the same order:
+    features of a handle created with PHDFX_FLAGS=1 equal those of a default handle, under plain launches (repeated — a
+    missed dependency would be a race) and under graph replay.  Links need full grids: n = 100 links layer3 only,
+    n >= 194 layer4 as well."""
+    plain = phdfx.B200Backbone(backbone, device=0, max_frames=n)
+    os.environ["PHDFX_FLAGS"] = "1"
+    try:
+        base = phdfx.B200Backbone(backbone, device=0, max_frames=n)
+    finally:
+        del os.environ["PHDFX_FLAGS"]
+    assert plain.linked_launches(n) == 0
+    links = base.linked_launches(n)
+    assert links >= (16 if n >= 194 else 10), links
+    assert base.linked_launches(8) == 0  # small grids: more than two launches could be resident at once
+    frames = torch.from_numpy(R.seeded_frames(n, 224, 224, 300 + n)).cuda()
+    want = plain.extract_u8(frames, None).clone()
+    out = torch.empty(n, 2048, device="cuda")
+    for _ in range(6):
+        out.fill_(float("nan"))
+        base.extract_u8(frames, None, out=out)
+        assert torch.equal(out, want), n
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        base.extract_u8(frames, None, out=out)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g):
+        base.extract_u8(frames, None, out=out)
+    for _ in range(6):
+        out.fill_(float("nan"))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want), n
+    del g
+    base.close()
+    plain.close()
+
+
 def test_small_batches_are_bit_identical_to_their_rows_in_a_big_batch(backbone):
     """Launches with few tiles use narrower N tiles (api.cu: geometry): a frame's features must not depend on it."""
     e = phdfx.B200Backbone(backbone, device=0, max_frames=64)

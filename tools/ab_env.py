@@ -1,7 +1,7 @@
 """A/B of one debug switch on the same box: alternates `VAR` unset / VAR=1 over fresh processes of tools/graph_test.py
 and prints the graph-replayed step time of each run and the medians.
 
-    python tools/ab_env.py PHDFX_NO_WPRE 3 [batch]
+    python tools/ab_env.py PHDFX_NO_WPRE 3 [batch [value ...]]      values default to: unset 1
 """
 import os
 import re
@@ -17,13 +17,14 @@ def main():
     var = sys.argv[1]
     rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     batch = sys.argv[3] if len(sys.argv) > 3 else "256"
-    res = {"unset": [], "1": []}
+    values = sys.argv[4:] or ["unset", "1"]
+    res = {v: [] for v in values}
     for r in range(rounds):
-        for val in ("unset", "1"):
+        for val in values:
             env = dict(os.environ)
             env.pop(var, None)
-            if val == "1":
-                env[var] = "1"
+            if val != "unset":
+                env[var] = val
             out = subprocess.run([sys.executable, str(ROOT / "tools" / "graph_test.py"), batch], env=env,
                                  capture_output=True, text=True, timeout=600)
             m = re.search(r"graph replay ([0-9.]+) us/step", out.stdout)
