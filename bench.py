@@ -529,7 +529,7 @@ def run_b200(args):
         cfg4 = config4_leg(eng, dev, rank, world)
 
     n_chain = sum(1 for i in range(len(eng.plan.layers)) if eng.chain_span(i) > 0)
-    n_trunk = graphs[0].launches - 1  # minus K1
+    n_trunk = trunk_graphs[0].launches  # phdfx_forward on an NHWC4p tensor: the stem without K1 inside
     sched, sched_flags = eng.get_schedule()
     if rank == 0:
         cpu = gpu_ref = None

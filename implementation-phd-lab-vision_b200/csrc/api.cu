@@ -93,6 +93,8 @@ struct phdfx {
   bool use_rev = true;              // PHDFX_NO_REV=1: every launch walks its tiles in ascending order
   bool use_halo = true;             // PHDFX_NO_HALO=1: 3x3/1 convs of layer1 / layer2 through the im2col path
   bool use_small_n = true;          // PHDFX_NO_SMALL_N=1: keep 256-wide N tiles for launches with few tiles
+  int fuse_k1 = 1;                  // K1 inside the stem kernel: 1 = where it pays (stem_can_fuse_k1), 0 = never
+                                    // (PHDFX_NO_FUSE_K1=1), 2 = whenever the rows fit (PHDFX_FUSE_K1=1; tests)
   bool use_flags = false;           // PHDFX_FLAGS=1: launches follow their predecessor's frame progress counters
   size_t flag_max_bytes = 64u << 20;  // PHDFX_FLAG_MAX_MB: larger tensors keep griddepcontrol.wait + serpentine order
   int real_sms = 0;                 // SMs of the device (num_sms may be capped for experiments)
@@ -622,6 +624,16 @@ int launch_chain(phdfx_t* h, const ChainPlan& cp, int n, cudaStream_t st, int re
   return launch_chain_t<56, 64, 256, false, 0>(h, cp, p, st);
 }
 
+// what feeds arena buffer 0 (the NHWC4p network input) during a pass over the schedule
+struct Source {
+  const void* d_in = nullptr;       // caller's NHWC4p tensor holding the call's n frames; nullptr = the arena's buffer 0
+  const uint8_t* frames = nullptr;  // non-null: K1 runs inside the schedule, in front of every wave of stage 0
+  int H = 0, W = 0;
+  const int32_t* boxes = nullptr;
+  int flip_w = 0;
+  const float* jitter = nullptr;
+};
+
 // Fused stem + max-pool (stem_pool_sm100.cuh).  `out` receives [n][56][56][64] bf16.
 int build_stem_pool_map(phdfx_t* h, void* out, int frames, CUtensorMap* m) {
   cuuint64_t d[2] = {64, static_cast<cuuint64_t>(frames) * kSpPool * kSpPool};
@@ -630,13 +642,31 @@ int build_stem_pool_map(phdfx_t* h, void* out, int frames, CUtensorMap* m) {
   return encode_tiled(h, m, out, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B, "stem+pool out");
 }
 
+// Should K1 run inside the stem kernel for frames of this size?  The converter warps' row staging must fit, and it
+// must pay: the stem kernel has few issue slots to spare, so the converters make it longer by about what K1 takes on
+// identity-size frames (whole step at batch 256, graph replay, B200: 224x224 +12 us, i.e. neutral, with 160 MB less
+// DRAM traffic and one launch less), lose on small frames that need the bilinear stencil (300x280, 241-pixel boxes:
+// +117 us) and win on camera-sized frames (1002x1000, 517-pixel boxes: -72 us), where K1 as a launch of its own waits
+// on long scattered source rows that the converters prefetch asynchronously.
+bool stem_can_fuse_k1(const phdfx_t* h, int H, int W) {
+  if (h->fuse_k1 == 0 || StemPoolSmem::fuse_total(W) + 1024 > 232448) return false;
+  return h->fuse_k1 == 2 || (H == kImg && W == kImg) || W >= 512;
+}
+
+// `u8`: non-null = FUSE_K1 launch on the n uint8 frames it describes (already offset to the launch's first frame)
 int launch_stem_pool(phdfx_t* h, const phdfx_layer_desc& L, const CUtensorMap& map_out, const void* in, int n,
-                     cudaStream_t st, bool zero_ctrs = false) {
+                     cudaStream_t st, bool zero_ctrs = false, const Source* u8 = nullptr) {
   static bool attr_set[64] = {};
-  const int smem = StemPoolSmem::TOTAL + 1024;
+  static int fuse_smem_set[64] = {};
+  const int smem = (u8 ? StemPoolSmem::fuse_total(u8->W) : StemPoolSmem::TOTAL) + 1024;
   if (!attr_set[h->device & 63]) {
-    CUDA_TRY(h, cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     StemPoolSmem::TOTAL + 1024));
     attr_set[h->device & 63] = true;
+  }
+  if (u8 && smem > fuse_smem_set[h->device & 63]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fuse_smem_set[h->device & 63] = smem;
   }
   StemPoolParams p{};
   p.in = static_cast<const __nv_bfloat16*>(in);
@@ -649,7 +679,30 @@ int launch_stem_pool(phdfx_t* h, const phdfx_layer_desc& L, const CUtensorMap& m
   }
   const int bands = n * kSpBandsPerFrame;
   const int grid = bands < h->num_sms ? bands : h->num_sms;
-  CUDA_TRY(h, launch_pdl(stem_pool_kernel, dim3(grid), dim3(kSpThreads), smem, st, map_out, p));
+  if (u8) {
+    p.frames = u8->frames;
+    p.H = u8->H;
+    p.W = u8->W;
+    p.boxes = u8->boxes;
+    p.flip_w = u8->flip_w;
+    static long long* d_stem_trace = nullptr;
+    if (getenv("PHDFX_STEM_TRACE")) {  // debug: phase clocks of one converter warp, printed after the launch (synchronises)
+      if (!d_stem_trace) cudaMalloc(&d_stem_trace, 8 * sizeof(long long));
+      cudaMemset(d_stem_trace, 0, 8 * sizeof(long long));
+      p.trace = d_stem_trace;
+    }
+    CUDA_TRY(h, launch_pdl(stem_pool_kernel<true>, dim3(grid), dim3(kSpFuseThreads), smem, st, map_out, p));
+    if (p.trace) {
+      long long t[8];
+      cudaDeviceSynchronize();
+      cudaMemcpy(t, p.trace, sizeof(t), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "stem converter warp 12 of CTA 0: %lld rows; cycles per row: issue %lld, wait copies %lld, wait slot %lld, "
+              "pixels %lld, fence+arrive %lld\n", t[5], t[0] / (t[5] ? t[5] : 1), t[1] / (t[5] ? t[5] : 1),
+              t[2] / (t[5] ? t[5] : 1), t[3] / (t[5] ? t[5] : 1), t[4] / (t[5] ? t[5] : 1));
+    }
+  } else {
+    CUDA_TRY(h, launch_pdl(stem_pool_kernel<false>, dim3(grid), dim3(kSpThreads), smem, st, map_out, p));
+  }
   h->last_launches++;
   return 0;
 }
@@ -744,7 +797,7 @@ int k1_launch(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const in
 // (dry = build the maps only).  *span = execution-list entries covered (a fused chain covers 2 or 3).
 int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, const void* ext_in, bool buf0_local,
                float* d_feats, cudaStream_t st, int rev, bool dry, int* span, const LaunchDep& dep = LaunchDep(),
-               bool zero_ctrs = false) {
+               bool zero_ctrs = false, const Source* u8 = nullptr) {
   const auto& L = h->layers[i];
   // frame f of a tensor lives at base + f * (the TENSOR's bytes per frame) — the dense layout an un-waved pass uses, so
   // a stage may read what a differently-waved stage wrote; wave-local tensors sit at frame 0 (+ slot) of their buffer
@@ -822,7 +875,7 @@ int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, cons
     maps = &cache.back().maps;
   }
   if (dry) return 0;
-  if (L.kind == PHDFX_STEM_POOL) return launch_stem_pool(h, L, maps->o, at(L.in_buf, in_bpf(L)), m, st, zero_ctrs);
+  if (L.kind == PHDFX_STEM_POOL) return launch_stem_pool(h, L, maps->o, at(L.in_buf, in_bpf(L)), m, st, zero_ctrs, u8);
   void* out = L.gap ? static_cast<void*>(d_feats + static_cast<size_t>(f0) * L.cout) : const_cast<void*>(k.out);
   return launch_conv(h, L, *maps, k.res, out, m, st, rev, nullptr, dep);
 }
@@ -870,16 +923,6 @@ std::vector<char> plan_links(const phdfx_t* h, int n) {
   return link;
 }
 
-// what feeds arena buffer 0 (the NHWC4p network input) during a pass over the schedule
-struct Source {
-  const void* d_in = nullptr;       // caller's NHWC4p tensor holding the call's n frames; nullptr = the arena's buffer 0
-  const uint8_t* frames = nullptr;  // non-null: K1 runs inside the schedule, in front of every wave of stage 0
-  int H = 0, W = 0;
-  const int32_t* boxes = nullptr;
-  int flip_w = 0;
-  const float* jitter = nullptr;
-};
-
 }  // namespace
 
 extern "C" {
@@ -914,6 +957,8 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   if (const char* e = getenv("PHDFX_NO_CG2")) h->use_cg2 = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_REV")) h->use_rev = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_SMALL_N")) h->use_small_n = !(e[0] == '1');
+  if (const char* e = getenv("PHDFX_FUSE_K1")) h->fuse_k1 = e[0] == '1' ? 2 : 1;
+  if (const char* e = getenv("PHDFX_NO_FUSE_K1")) h->fuse_k1 = e[0] == '1' ? 0 : h->fuse_k1;
   if (const char* e = getenv("PHDFX_FLAGS")) h->use_flags = e[0] == '1';
   if (const char* e = getenv("PHDFX_FLAG_MAX_MB")) h->flag_max_bytes = static_cast<size_t>(atoi(e)) << 20;
   h->real_sms = prop.multiProcessorCount;
@@ -1112,7 +1157,16 @@ static int forward_impl(phdfx_t* h, const Source& src, int n, float* d_feats, cu
       if (done[s] < n && done[s - 1] >= ends[s][idx[s]]) break;
     const Stage& sg = h->stages[s];
     const int f0 = done[s], m = ends[s][idx[s]] - f0;
-    if (s == 0 && src.frames != nullptr) {
+    // K1 inside the stem kernel: plain (not colour-jittered) uint8 frames whose rows fit the converters' staging
+    const bool fuse_k1 = src.frames != nullptr && src.jitter == nullptr && h->layers[0].kind == PHDFX_STEM_POOL &&
+                         stem_can_fuse_k1(h, src.H, src.W);
+    Source wave_src;
+    if (fuse_k1) {
+      wave_src = src;
+      wave_src.frames = src.frames + static_cast<size_t>(f0) * src.H * src.W * 3;
+      wave_src.boxes = src.boxes ? src.boxes + 4 * static_cast<size_t>(f0) : nullptr;
+    }
+    if (s == 0 && src.frames != nullptr && !fuse_k1) {
       char* out0 = static_cast<char*>(h->bufs[0]) + (buf0_local ? 0 : static_cast<size_t>(f0) * h->buf_bytes[0]);
       mark(-1);
       if (int rc = k1_launch(h, src.frames + static_cast<size_t>(f0) * src.H * src.W * 3, m, src.H, src.W,
@@ -1140,7 +1194,7 @@ static int forward_impl(phdfx_t* h, const Source& src, int n, float* d_feats, cu
         dep.sig = h->d_ctrs + static_cast<size_t>(i) * (h->max_frames + 1);
       if (h->d_cta_ts) dep.cta_ts = h->d_cta_ts + static_cast<size_t>(i) * kTraceCtas * 6;
       if (int rc = run_launch(h, sg, i, f0, m, 0, src.d_in, buf0_local, d_feats, st, rev, false, &span, dep,
-                              any_link && i == 0))
+                              any_link && i == 0, (fuse_k1 && i == 0) ? &wave_src : nullptr))
         return rc;
       for (int j = i; j < i + span; ++j)
         if (h->layers[j].gap) wrote_feats = true;

@@ -127,6 +127,138 @@ __device__ __forceinline__ void jit_apply(float (&c)[3], const float* __restrict
   }
 }
 
+// ---- per-row pieces of K1, shared by preprocess_u8_kernel and by the stem kernel's converter warps (stem_pool_sm100.cuh,
+// FUSE_K1: the same rows are produced straight into the stem's shared-memory ring, no NHWC4p tensor in HBM) ----------
+struct K1Box {        // per frame
+  int top, left, bh, bw;  // crop, clamped to the frame
+  float scale_h, scale_w;
+};
+struct K1Row {        // per output row
+  const uint8_t* r0;  // first byte of source row y0 of the crop (bytes [left*3, (left+bw)*3) of the frame row)
+  const uint8_t* r1;  // same for row y1
+  int bh, bw;         // crop size after clamping to the frame
+  float ly0, ly1;     // vertical weights
+  bool need1;         // row y1 carries weight (weight-0 taps add exactly +0: identity-size crops skip it)
+};
+// crop box of frame n, clamped to the frame as the reference's slicing `frames[:, top:top+h, left:left+w]`
+// (src/dataset.py:146) cuts it; row staging is sized from W and relies on left + bw <= W
+__device__ __forceinline__ K1Box k1_box(int n, int H, int W, const int32_t* __restrict__ boxes) {
+  K1Box b;
+  b.top = 0, b.left = 0, b.bh = H, b.bw = W;
+  if (boxes != nullptr) {
+    b.top = boxes[4 * n + 0];
+    b.left = boxes[4 * n + 1];
+    b.bh = boxes[4 * n + 2];
+    b.bw = boxes[4 * n + 3];
+    b.top = min(max(b.top, 0), H - 1);
+    b.left = min(max(b.left, 0), W - 1);
+    b.bh = min(max(b.bh, 1), H - b.top);
+    b.bw = min(max(b.bw, 1), W - b.left);
+  }
+  b.scale_h = __fdiv_rn(static_cast<float>(b.bh), static_cast<float>(kImg));
+  b.scale_w = __fdiv_rn(static_cast<float>(b.bw), static_cast<float>(kImg));
+  return b;
+}
+// the vertical stencil of output row y of frame n
+__device__ __forceinline__ K1Row k1_row(const uint8_t* __restrict__ frames, const K1Box& b, int n, int y, int H, int W) {
+  K1Row g;
+  g.bh = b.bh;
+  g.bw = b.bw;
+  float sy = __fmaf_rn(b.scale_h, static_cast<float>(y) + 0.5f, -0.5f);
+  sy = sy < 0.0f ? 0.0f : sy;
+  int y0 = static_cast<int>(sy);
+  y0 = y0 > g.bh - 1 ? g.bh - 1 : y0;
+  const int y1 = y0 + (y0 < g.bh - 1 ? 1 : 0);
+  g.ly1 = __fsub_rn(sy, static_cast<float>(y0));
+  g.ly1 = fminf(fmaxf(g.ly1, 0.0f), 1.0f);
+  g.ly0 = __fsub_rn(1.0f, g.ly1);
+  const uint8_t* base = frames + static_cast<size_t>(n) * H * W * 3;
+  g.r0 = base + (static_cast<size_t>(b.top + y0) * W + b.left) * 3;
+  g.r1 = base + (static_cast<size_t>(b.top + y1) * W + b.left) * 3;
+  g.need1 = g.ly1 != 0.0f;
+  return g;
+}
+// the [3][256] table of final bf16 values: /255 and Normalize in the reference's fp32 operations
+__device__ __forceinline__ void k1_build_lut(__nv_bfloat16* lut, int tid, int nthreads) {
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int i = tid; i < 3 * 256; i += nthreads) {
+    const int c = i >> 8;
+    const float x01 = __fdiv_rn(static_cast<float>(i & 255), 255.0f);             // frames.to(float32) / 255.0
+    lut[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]));    // Normalize, then bf16
+  }
+}
+// One NHWC4p pixel (4 x bf16: three channels + zero) of output column x in [0, 224) from the staged source rows.
+// IDENT: a 224x224 crop — F.resize returns its input untouched (torchvision transforms/functional.py:470-471); the
+// bilinear stencil degenerates to weight 1 on v00 and +0 elsewhere, i.e. the same bytes: table lookups only.
+// Both variants are branch-free so that the seven pixels a lane produces per row overlap their shared-memory loads.
+template <bool IDENT>
+__device__ __forceinline__ uint2 k1_plain_pixel(const uint8_t* t0, const uint8_t* t1, const K1Row& g, float scale_w,
+                                                int flip_w, const __nv_bfloat16* lut, int x) {
+  const uint16_t* l16 = reinterpret_cast<const uint16_t*>(lut);
+  uint2 o;
+  x = flip_w ? kImg - 1 - x : x;
+  if (IDENT) {
+    const uint32_t r0v = l16[t0[x * 3 + 0]], r1v = l16[256 + t0[x * 3 + 1]], r2v = l16[512 + t0[x * 3 + 2]];
+    o.x = r0v | (r1v << 16);
+    o.y = r2v;
+    return o;
+  }
+  float sx = __fmaf_rn(scale_w, static_cast<float>(x) + 0.5f, -0.5f);
+  sx = sx < 0.0f ? 0.0f : sx;
+  int x0 = static_cast<int>(sx);
+  x0 = x0 > g.bw - 1 ? g.bw - 1 : x0;
+  const int x1 = x0 + (x0 < g.bw - 1 ? 1 : 0);
+  float lx1 = __fsub_rn(sx, static_cast<float>(x0));
+  lx1 = fminf(fmaxf(lx1, 0.0f), 1.0f);
+  const float lx0 = __fsub_rn(1.0f, lx1);
+  const float w00 = __fmul_rn(g.ly0, lx0), w01 = __fmul_rn(g.ly0, lx1);
+  const float w10 = __fmul_rn(g.ly1, lx0), w11 = __fmul_rn(g.ly1, lx1);
+  uint32_t r[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v00 = static_cast<float>(t0[x0 * 3 + c]);
+    const float v01 = static_cast<float>(t0[x1 * 3 + c]);
+    const float v10 = static_cast<float>(t1[x0 * 3 + c]);
+    const float v11 = static_cast<float>(t1[x1 * 3 + c]);
+    const float v = __fmaf_rn(w11, v11, __fmaf_rn(w10, v10, __fmaf_rn(w00, v00, __fmul_rn(w01, v01))));
+    const int u8 = static_cast<int>(fminf(fmaxf(rintf(v), 0.0f), 255.0f));  // round half to even, uint8 range
+    r[c] = l16[c * 256 + u8];
+  }
+  o.x = r[0] | (r[1] << 16);
+  o.y = r[2];
+  return o;
+}
+// the 224 image pixels of one output row, seven per lane (x = lane + 32 i); dst points at pixel x = 0
+template <bool IDENT>
+__device__ __forceinline__ void k1_plain_row(const uint8_t* t0, const uint8_t* t1, const K1Row& g, float scale_w,
+                                             int flip_w, const __nv_bfloat16* lut, uint2* dst, int lane) {
+  uint2 o[kImg / 32];
+  if (IDENT) {
+    // all 21 source bytes first, then the 21 table lookups: two shared-memory round trips per row instead of fourteen
+    const uint16_t* l16 = reinterpret_cast<const uint16_t*>(lut);
+    const uint8_t* tp = t0 + (flip_w ? (kImg - 1 - lane) * 3 : lane * 3);
+    const int step = flip_w ? -96 : 96;
+    uint32_t v[kImg / 32][3];
+#pragma unroll
+    for (int i = 0; i < kImg / 32; ++i) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[i][c] = tp[i * step + c];
+    }
+#pragma unroll
+    for (int i = 0; i < kImg / 32; ++i) {
+      const uint32_t r0v = l16[v[i][0]], r1v = l16[256 + v[i][1]], r2v = l16[512 + v[i][2]];
+      o[i].x = r0v | (r1v << 16);
+      o[i].y = r2v;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kImg / 32; ++i) o[i] = k1_plain_pixel<false>(t0, t1, g, scale_w, flip_w, lut, lane + 32 * i);
+  }
+#pragma unroll
+  for (int i = 0; i < kImg / 32; ++i) dst[lane + 32 * i] = o[i];
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kK1Warps * 32)
 preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
@@ -144,11 +276,7 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
   __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(s_rows);  // [3][256] (KIND_PLAIN)
   float* lut01 = reinterpret_cast<float*>(s_rows);                // [256] u8 / 255 (jitter kinds; same 1536 bytes)
   if (KIND == KIND_PLAIN) {
-    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
-      const int c = i >> 8;
-      const float x01 = __fdiv_rn(static_cast<float>(i & 255), 255.0f);             // frames.to(float32) / 255.0
-      lut[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(x01, mean[c]), stdv[c]));    // Normalize, then bf16
-    }
+    k1_build_lut(lut, threadIdx.x, blockDim.x);
   } else {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut01[i] = __fdiv_rn(static_cast<float>(i), 255.0f);
   }
@@ -161,35 +289,15 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
   for (int rowi = blockIdx.x * kK1Warps + warp; rowi < total_rows; rowi += gridDim.x * kK1Warps) {
     const int n = rowi / kImg;
     const int y = rowi - n * kImg;
-    int top = 0, left = 0, bh = H, bw = W;
-    if (boxes != nullptr) {
-      top = boxes[4 * n + 0];
-      left = boxes[4 * n + 1];
-      bh = boxes[4 * n + 2];
-      bw = boxes[4 * n + 3];
-      // a box that leaves the frame is cut back to it, as the reference's slicing `frames[:, top:top+h, left:left+w]`
-      // (src/dataset.py:146) cuts it; row staging below is sized from W and relies on left + bw <= W
-      top = min(max(top, 0), H - 1);
-      left = min(max(left, 0), W - 1);
-      bh = min(max(bh, 1), H - top);
-      bw = min(max(bw, 1), W - left);
-    }
-    const float scale_h = __fdiv_rn(static_cast<float>(bh), static_cast<float>(kImg));
-    float sy = __fmaf_rn(scale_h, static_cast<float>(y) + 0.5f, -0.5f);
-    sy = sy < 0.0f ? 0.0f : sy;
-    int y0 = static_cast<int>(sy);
-    y0 = y0 > bh - 1 ? bh - 1 : y0;
-    const int y1 = y0 + (y0 < bh - 1 ? 1 : 0);
-    float ly1 = __fsub_rn(sy, static_cast<float>(y0));
-    ly1 = fminf(fmaxf(ly1, 0.0f), 1.0f);
-    const float ly0 = __fsub_rn(1.0f, ly1);
-    // stage rows y0 (and y1 when it carries weight) of the crop: bytes [left*3, (left+bw)*3) of the frame row
-    const uint8_t* base = frames + static_cast<size_t>(n) * H * W * 3;
-    const uint8_t* r0 = base + (static_cast<size_t>(top + y0) * W + left) * 3;
-    const uint8_t* r1 = base + (static_cast<size_t>(top + y1) * W + left) * 3;
+    const K1Box box = k1_box(n, H, W, boxes);
+    const K1Row geo = k1_row(frames, box, n, y, H, W);
+    const int bh = geo.bh, bw = geo.bw;
+    const float ly0 = geo.ly0, ly1 = geo.ly1;
+    const uint8_t* r0 = geo.r0;
+    const uint8_t* r1 = geo.r1;
     const int off0 = static_cast<int>(reinterpret_cast<uintptr_t>(r0) & 15);
     const int off1 = static_cast<int>(reinterpret_cast<uintptr_t>(r1) & 15);
-    const bool need1 = ly1 != 0.0f;  // weight-0 taps add exactly +0: skip the second row (identity-size crops)
+    const bool need1 = geo.need1;
     __syncwarp();                    // the previous row's readers are done with s0 / s1
     for (int pass = 0; pass < (need1 ? 2 : 1); ++pass) {
       const uint8_t* src = (pass == 0 ? r0 - off0 : r1 - off1);  // 16-byte aligned
@@ -207,10 +315,18 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
     __syncwarp();
     const uint8_t* t0 = s0 + off0;
     const uint8_t* t1 = need1 ? s1 + off1 : t0;
-    const float scale_w = __fdiv_rn(static_cast<float>(bw), static_cast<float>(kImg));
-    // a 224x224 crop: F.resize returns its input untouched (torchvision transforms/functional.py:470-471); the stencil
-    // below degenerates to weight 1 on v00 and +0 elsewhere, i.e. the same bytes — skip the arithmetic
+    const float scale_w = box.scale_w;
     const bool ident = (bh == kImg) && (bw == kImg) && KIND == KIND_PLAIN;
+    if (KIND == KIND_PLAIN) {
+      uint2* out_row = reinterpret_cast<uint2*>(out) + static_cast<size_t>(rowi) * kStemWPad;
+      if (ident)
+        k1_plain_row<true>(t0, t1, geo, scale_w, flip_w, lut, out_row + kStemLeftPad, lane);
+      else
+        k1_plain_row<false>(t0, t1, geo, scale_w, flip_w, lut, out_row + kStemLeftPad, lane);
+      if (lane < 2 * kStemLeftPad)  // the zero pad pixels left and right of the image
+        out_row[lane < kStemLeftPad ? lane : kImg + lane] = make_uint2(0u, 0u);
+      continue;
+    }
     const float* prm = KIND != KIND_PLAIN ? jitter + static_cast<size_t>(n) * kJitterFloats : nullptr;
     float mean_gray = 0.0f;
     if (KIND == KIND_JITTER) {  // sum of the frame's 224 row sums, in double, fixed order
@@ -224,13 +340,7 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, in
     for (int wp = lane; wp < kStemWPad; wp += 32) {
       uint2 o = make_uint2(0u, 0u);
       int x = wp - kStemLeftPad;
-      if (x >= 0 && x < kImg && ident) {
-        if (flip_w) x = kImg - 1 - x;
-        const uint16_t* l16 = reinterpret_cast<const uint16_t*>(lut);
-        const uint32_t r0v = l16[t0[x * 3 + 0]], r1v = l16[256 + t0[x * 3 + 1]], r2v = l16[512 + t0[x * 3 + 2]];
-        o.x = r0v | (r1v << 16);
-        o.y = r2v;
-      } else if (x >= 0 && x < kImg) {
+      if (x >= 0 && x < kImg) {
         if (flip_w) x = kImg - 1 - x;
         float sx = __fmaf_rn(scale_w, static_cast<float>(x) + 0.5f, -0.5f);
         sx = sx < 0.0f ? 0.0f : sx;

@@ -20,7 +20,15 @@
 //             away; only lane 0's left neighbour crosses a warp (64 B exchange slot) — and the pooled row goes straight
 //             to the store staging.  The conv rows never touch shared memory, which the N=64 MMAs' operand reads
 //             keep busy.  No ReLU instruction anywhere: the max starts at 0 and max(0, max(v)) == max-pool(relu(v)).
+//
+// FUSE_K1 (template): K1 — uint8 crop + bilinear resize + normalise (elementwise_sm100.cuh) — runs inside this kernel.
+// Four more warps ("converters") read the uint8 source rows (cp.async, double-buffered per warp), produce the bf16
+// NHWC4p rows with K1's own per-pixel function and write them straight into the ring slots the MMA warp reads; the
+// 106 MB NHWC4p tensor (write + read per 256 frames) and K1's launch disappear.  The zero pad pixels of a ring row are
+// written once, at kernel start.  Registers: 512 threads leave 128 per thread, the epilogue warps need ~170, so the
+// warpgroups re-balance with setmaxnreg (producer / MMA / store warps 56, converters 104, epilogue 176).
 #pragma once
+#include "elementwise_sm100.cuh"
 #include "ptx_sm100.cuh"
 
 namespace phdfxk {
@@ -38,6 +46,8 @@ constexpr int kSpPoolRowBytes = 8192;           // staging pitch (56 x 128 B = 7
 constexpr int kSpWeightBase = 7 * 4096;
 constexpr int kSpWeightBytes = kSpWeightBase + 5 * 8192;
 constexpr int kSpThreads = 384;
+constexpr int kSpFuseThreads = 512;   // + one warpgroup of converters
+constexpr int kSpConvWarps = 4;
 constexpr int kSpEpiThreads = 256;
 constexpr int kSpEpiWarps = 8;
 
@@ -50,6 +60,10 @@ struct StemPoolSmem {
   static constexpr int BARS = BIAS + 256;
   static constexpr int XCHG = BARS + 512;                                  // [2 parities][2 halves][4 quadrants][64 B]
   static constexpr int TOTAL = XCHG + 1024;
+  // FUSE_K1 only: the [3][256] bf16 table, then per converter warp 2 buffers x 2 source rows of row_cap bytes
+  static constexpr int LUT = TOTAL;
+  static constexpr int STAGE = LUT + kK1LutBytes;
+  static constexpr int fuse_total(int W) { return STAGE + kSpConvWarps * 4 * ((3 * W + 32 + 15) & ~15); }
 };
 static_assert(StemPoolSmem::WEIGHTS % 1024 == 0 && StemPoolSmem::POOL % 1024 == 0,
               "swizzled regions must be 1024-byte aligned");
@@ -61,7 +75,30 @@ struct StemPoolParams {
   int n_frames;
   uint32_t* zero_ptr;            // frame progress counters of the pass this launch opens (conv_igemm_sm100.cuh), or
   int zero_words;                // nullptr: zeroed here, behind this launch's full grid dependency
+  // FUSE_K1: the call's uint8 frames [n][H][W][3], crop boxes (nullable) and the mirror flag, as preprocess_u8_kernel
+  const uint8_t* frames;
+  int H, W;
+  const int32_t* boxes;
+  int flip_w;
+  long long* trace;  // debug (PHDFX_STEM_TRACE): converter warp 12 of CTA 0 accumulates clock64 per phase, [8]
 };
+
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 // executed by a whole converged warp; one elected lane issues (keeps operands in uniform registers)
 __device__ __forceinline__ void bulk_load_elect(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -94,8 +131,10 @@ struct Band {
   __device__ __forceinline__ int pairs() const { return j_last - j_first + 1; }
 };
 
-__global__ void __launch_bounds__(kSpThreads, 1)
+template <bool FUSE_K1>
+__global__ void __launch_bounds__(FUSE_K1 ? kSpFuseThreads : kSpThreads, 1)
 stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams p) {
+  constexpr int NTHREADS = FUSE_K1 ? kSpFuseThreads : kSpThreads;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = StemPoolSmem;
@@ -114,12 +153,18 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
   const int num_bands = p.n_frames * kSpBandsPerFrame;
 
   // zero slot, bias
-  for (int i = threadIdx.x; i < (kSpRowPitch + 1024) / 16; i += kSpThreads)
+  for (int i = threadIdx.x; i < (kSpRowPitch + 1024) / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(smem + L::ZERO)[i] = make_uint4(0, 0, 0, 0);
+  if (FUSE_K1) {
+    // ring rows: the converters only ever write the 224 image pixels of a row; its pad pixels stay zero from here on
+    for (int i = threadIdx.x; i < kSpPairSlots * 2 * kSpRowPitch / 16; i += NTHREADS)
+      reinterpret_cast<uint4*>(smem + L::RING)[i] = make_uint4(0, 0, 0, 0);
+    k1_build_lut(reinterpret_cast<__nv_bfloat16*>(smem + L::LUT), threadIdx.x, NTHREADS);
+  }
   if (threadIdx.x < 64) s_bias[threadIdx.x] = __ldg(&p.bias[threadIdx.x]);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kSpPairSlots; ++i) {
-      mbar_init(&pair_full[i], 1);
+      mbar_init(&pair_full[i], FUSE_K1 ? 2 : 1);  // FUSE_K1: one arrive per converted row of the pair
       mbar_init(&pair_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -144,15 +189,19 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
   griddep_launch_dependents();  // PDL: see conv_igemm_sm100.cuh
   griddep_wait();
   if (p.zero_ptr != nullptr)
-    for (int i = blockIdx.x * kSpThreads + threadIdx.x; i < p.zero_words; i += gridDim.x * kSpThreads) p.zero_ptr[i] = 0u;
+    for (int i = blockIdx.x * NTHREADS + threadIdx.x; i < p.zero_words; i += gridDim.x * NTHREADS) p.zero_ptr[i] = 0u;
 
+  // Role dispatch by warpgroup, so that each setmaxnreg is ONE instruction executed by the four warps of its warpgroup
+  // and dominates the code whose register budget it sets.
+  if (warp < 4) {
+  if (FUSE_K1) setmaxnreg_dec<56>();
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (whole warp, uniform flow)
     {
       mbar_arrive_expect_tx_elect(w_full, kSpWeightBytes);
       bulk_load_elect(smem + L::WEIGHTS, p.weights, kSpWeightBytes, w_full);
       int seq = 0;
-      for (int b = blockIdx.x; b < num_bands; b += gridDim.x) {
+      for (int b = blockIdx.x; !FUSE_K1 && b < num_bands; b += gridDim.x) {
         const Band band(b);
         const uint8_t* frame = reinterpret_cast<const uint8_t*>(p.in) +
                                static_cast<size_t>(band.n) * kSpIn * kSpRowBytes;
@@ -269,7 +318,134 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
       }
       tma_store_wait_read<0>();  // the CTA may exit once its stores have left shared memory (conv_igemm_sm100.cuh)
     }
-  } else if (warp >= 4) {
+  }
+  } else if (FUSE_K1 && warp >= 12) {
+    setmaxnreg_dec<104>();
+    // ------------------------------------------------------------------ converters (warps 12..15): K1 into the ring
+    // Ring rows in sequence order are (pair seq, parity); warp cw takes pairs with seq % 2 == cw / 2 and parity cw % 2.
+    const int cw = warp - 12;
+    const int par = cw & 1;
+    const int row_cap = (3 * p.W + 32 + 15) & ~15;
+    uint8_t* stage = smem + L::STAGE + cw * 4 * row_cap;  // [2 buffers][2 source rows][row_cap]
+    const __nv_bfloat16* lut = reinterpret_cast<const __nv_bfloat16*>(smem + L::LUT);
+    const uint8_t* buf_begin = p.frames;
+    const uint8_t* buf_end = p.frames + static_cast<size_t>(p.n_frames) * p.H * p.W * 3;
+    // cursor over this warp's rows: band b, pair j, ring sequence number seq
+    int cb = blockIdx.x, cj = 0, cseq = 0;
+    bool band_open = false;
+    int cj_last = 0, cn = 0;
+    auto next_row = [&](int* n, int* h, int* seq) -> bool {
+      for (;;) {
+        if (!band_open) {
+          if (cb >= num_bands) return false;
+          const Band band(cb);
+          cj = band.j_first;
+          cj_last = band.j_last;
+          cn = band.n;
+          band_open = true;
+        }
+        if (cj > cj_last) {
+          band_open = false;
+          cb += gridDim.x;
+          continue;
+        }
+        const int s = cseq++;
+        const int j = cj++;
+        if ((s & 1) == (cw >> 1)) {
+          *n = cn;
+          *h = 2 * j + par;
+          *seq = s;
+          return true;
+        }
+      }
+    };
+    // stage the source row(s) of output row h of frame n into buffer `bsel` (asynchronous copies, one commit group)
+    int box_n = -1;
+    K1Box box;
+    auto issue = [&](int n, int h, int bsel) -> K1Row {
+      if (n != box_n) {  // per frame: the crop box and its two scale factors (IEEE divisions)
+        box = k1_box(n, p.H, p.W, p.boxes);
+        box_n = n;
+      }
+      const K1Row g = k1_row(p.frames, box, n, h, p.H, p.W);
+      for (int pass = 0; pass < (g.need1 ? 2 : 1); ++pass) {
+        const uint8_t* r = pass == 0 ? g.r0 : g.r1;
+        const int off = static_cast<int>(reinterpret_cast<uintptr_t>(r) & 15);
+        const uint8_t* src = r - off;
+        uint8_t* dst = stage + (bsel * 2 + pass) * row_cap;
+        const int nvec = (off + g.bw * 3 + 15) >> 4;
+        if (src >= buf_begin && src + 16 * nvec <= buf_end) {
+          for (int i = lane; i < nvec; i += 32) cp_async_16(dst + 16 * i, src + 16 * i);
+        } else {  // the first / last row of the whole buffer: its first / last vector must stay inside it
+          for (int i = lane; i < nvec; i += 32) {
+            const uint8_t* gp = src + 16 * i;
+            if (gp >= buf_begin && gp + 16 <= buf_end) {
+              cp_async_16(dst + 16 * i, gp);
+            } else {
+              for (int k = 0; k < 16; ++k) dst[16 * i + k] = (gp + k >= buf_begin && gp + k < buf_end) ? gp[k] : 0;
+            }
+          }
+        }
+      }
+      cp_async_commit();
+      return g;
+    };
+    long long tr[6] = {0, 0, 0, 0, 0, 0};
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0 && cw == 0;
+    auto tick = [&](int k, long long& t) {
+      if (tracing) {
+        const long long now = clock64();
+        tr[k] += now - t;
+        t = now;
+      }
+    };
+    long long tt = clock64();
+    int n0, h0, s0, n1 = 0, h1 = 0, s1 = 0;
+    bool have = next_row(&n0, &h0, &s0);
+    int bsel = 0;
+    K1Row g0, g1;
+    if (have) g0 = issue(n0, h0, 0);
+    while (have) {
+      const bool have_next = next_row(&n1, &h1, &s1);
+      if (have_next) {
+        __syncwarp();  // the readers of buffer bsel ^ 1 (two rows ago) are done
+        g1 = issue(n1, h1, bsel ^ 1);
+        tick(0, tt);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      tick(1, tt);
+      const int off0 = static_cast<int>(reinterpret_cast<uintptr_t>(g0.r0) & 15);
+      const int off1 = static_cast<int>(reinterpret_cast<uintptr_t>(g0.r1) & 15);
+      const uint8_t* t0 = stage + (bsel * 2 + 0) * row_cap + off0;
+      const uint8_t* t1 = g0.need1 ? stage + (bsel * 2 + 1) * row_cap + off1 : t0;
+      // (scale_w of the row being converted: rows of a band share the frame, a band switch recomputes it exactly)
+      const float scale_w = __fdiv_rn(static_cast<float>(g0.bw), static_cast<float>(kImg));
+      const bool ident = (g0.bh == kImg) && (g0.bw == kImg);
+      const int slot = s0 % kSpPairSlots;
+      mbar_wait(&pair_empty[slot], ((s0 / kSpPairSlots) & 1) ^ 1);
+      tick(2, tt);
+      uint2* dst = reinterpret_cast<uint2*>(smem + L::RING + slot * 2 * kSpRowPitch + par * kSpRowPitch) + kStemLeftPad;
+      if (ident)
+        k1_plain_row<true>(t0, t1, g0, scale_w, p.flip_w, lut, dst, lane);
+      else
+        k1_plain_row<false>(t0, t1, g0, scale_w, p.flip_w, lut, dst, lane);
+      tick(3, tt);
+      fence_proxy_async_smem();  // generic-proxy writes -> the tensor core's operand reads (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pair_full[slot]);
+      tick(4, tt);
+      if (tracing) ++tr[5];
+      have = have_next;
+      n0 = n1, h0 = h1, s0 = s1, g0 = g1;
+      bsel ^= 1;
+    }
+    if (tracing && lane == 0)
+      for (int k = 0; k < 6; ++k) p.trace[k] = tr[k];
+  } else if (warp < 12) {
+    if (FUSE_K1) setmaxnreg_inc<176>();
     // ------------------------------------------------------------------ epilogue + pool (warps 4..11)
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;  // 32-channel half of the 64 output channels

@@ -294,7 +294,7 @@ def test_chains_are_bit_identical_to_per_conv_kernels(backbone):
         del os.environ["PHDFX_NO_CHAIN"]
     a = fused.extract_u8(frames, None)
     b = plain.extract_u8(frames, None)
-    assert fused.launches == 41 and plain.launches == 50
+    assert fused.launches == 40 and plain.launches == 49
     assert torch.equal(a, b)
     fused.close()
     plain.close()
@@ -310,13 +310,13 @@ def test_unfused_stem_and_maxpool_kernels(backbone, n):
     frames = torch.from_numpy(R.seeded_frames(n, 224, 224, 31)).cuda()
     a = fused.extract_u8(frames, None)
     b = unfused.extract_u8(frames, None)
-    assert fused.launches == 41 and unfused.launches == 42
+    assert fused.launches == 40 and unfused.launches == 42  # K1 rides in the fused stem kernel only
     err, cos = frame_errors(b.cpu().numpy(), a.cpu().numpy())
     assert err.max() < 5e-3 and cos.min() > 0.99999
     # separate down-sample launches + residual add (rounds the branch to bf16 first): same features within bf16 noise
     plain = phdfx.B200Backbone(backbone, device=0, max_frames=4, fuse_downsample=False)
     c = plain.extract_u8(frames, None)
-    assert plain.launches == 47
+    assert plain.launches == 46
     err, cos = frame_errors(c.cpu().numpy(), a.cpu().numpy())
     assert err.max() < 1e-2 and cos.min() > 0.9999
     plain.close()
@@ -464,7 +464,7 @@ def test_cuda_graph_replay_is_bit_identical(eng):
     assert torch.equal(g.replay(), eng.extract_u8(frames[:10].contiguous(), boxes[:10].contiguous()))
     buf.copy_(frames[10:])
     assert torch.equal(g.replay(), eng.extract_u8(frames[10:].contiguous(), boxes[10:].contiguous()))
-    assert g.launches == 41
+    assert g.launches == 41  # 240x250 frames: K1 stays a launch of its own (api.cu: stem_can_fuse_k1)
 
 
 def test_errors_are_loud(eng):
@@ -493,9 +493,9 @@ def test_full_batch_256_properties():
     waved_launches = e.launches
     e.set_waves(((0, 0),))
     whole = e.extract_u8(frames, None)
-    # un-waved: K1 + fused stem/maxpool + 39 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 ->
+    # un-waved: fused K1/stem/maxpool + 39 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 ->
     # next conv1 chains and layer2's conv2 -> conv3 chains are one launch each), all ours
-    assert e.launches == 41 and waved_launches >= 41
+    assert e.launches == 40 and waved_launches >= 40
     assert torch.equal(big, whole)
     small = torch.cat([e.extract_u8(frames[i:i + 37].contiguous(), None) for i in range(0, 256, 37)])
     assert torch.equal(big, small)
@@ -535,7 +535,7 @@ def test_config5_fixture_is_what_head_extracts(golden_dir):
 
 
 @pytest.mark.parametrize("switch,exact", [("PHDFX_NO_CG2", True), ("PHDFX_NO_REV", True), ("PHDFX_NO_SMALL_N", True),
-                                          ("PHDFX_NO_HALO", False)])
+                                          ("PHDFX_NO_FUSE_K1", True), ("PHDFX_NO_HALO", False)])
 def test_kernel_selection_switches(backbone, switch, exact):
     """The A/B switches select other kernels for the same layers (1-CTA instead of CTA-pair implicit GEMM, ascending tile
     order, 256-wide N tiles for small launches, im2col instead of the halo patch mode).  They are read per handle at
@@ -559,6 +559,57 @@ def test_kernel_selection_switches(backbone, switch, exact):
             assert err.max() < 5e-3 and cos.min() > 0.99999, (switch, n, err.max())
     for e in (base, alt, again):
         e.close()
+
+
+@pytest.mark.parametrize("H,W,box,flip,n", [
+    (224, 224, None, False, 9),                 # identity-size frames: the table-lookup path
+    (224, 224, None, True, 5),                  # mirrored read
+    (300, 280, (20, 30, 217, 217), False, 7),   # bilinear, odd byte alignment of the crop rows
+    (241, 263, "ragged", True, 13),             # a different box per frame, mirrored
+    (1002, 1000, (100, 200, 517, 517), False, 3),   # H36M-sized frames (3 KB staging rows)
+    (64, 48, None, False, 6),                   # 4.7x upscale: many rows share source rows
+])
+def test_k1_inside_the_stem_equals_k1_as_a_launch(backbone, H, W, box, flip, n):
+    """extract_u8 runs K1 inside the stem kernel's converter warps (stem_pool_sm100.cuh, FUSE_K1) with the very device
+    function preprocess_u8_kernel uses (pinned bit for bit against the reference's own crop/resize/normalise above): the
+    features equal those of K1 as a launch of its own (PHDFX_NO_FUSE_K1=1) bit for bit, for every crop geometry, also
+    in frame waves (the fused launch then starts at a frame offset of the caller's buffer) and at the first / last
+    vector of the buffer (frames sliced out of a larger allocation at odd byte offsets)."""
+    os.environ["PHDFX_FUSE_K1"] = "1"  # for every geometry (the default only fuses where it is not slower, api.cu)
+    try:
+        fused = phdfx.B200Backbone(backbone, device=0, max_frames=16)
+    finally:
+        del os.environ["PHDFX_FUSE_K1"]
+    os.environ["PHDFX_NO_FUSE_K1"] = "1"
+    try:
+        plain = phdfx.B200Backbone(backbone, device=0, max_frames=16)
+    finally:
+        del os.environ["PHDFX_NO_FUSE_K1"]
+    raw = torch.from_numpy(R.seeded_frames(n, H, W, 900 + H + n)).cuda()
+    boxes = None
+    if box == "ragged":
+        g = np.random.default_rng(H + W)
+        rows = []
+        for _ in range(n):
+            side = int(g.integers(40, min(H, W)))
+            rows.append((int(g.integers(0, H - side + 1)), int(g.integers(0, W - side + 1)), side, side))
+        boxes = torch.tensor(rows, dtype=torch.int32, device="cuda")
+    elif box is not None:
+        boxes = torch.tensor([box] * n, dtype=torch.int32, device="cuda")
+    a = fused.extract_u8(raw, boxes, flip_w=flip)
+    assert fused.launches == 40
+    b = plain.extract_u8(raw, boxes, flip_w=flip)
+    assert plain.launches == 41
+    assert torch.equal(a, b)
+    # frames that do not start at an aligned address / end at the end of an allocation
+    pad = torch.zeros(raw.numel() + 7, dtype=torch.uint8, device="cuda")
+    pad[7:] = raw.flatten()
+    shifted = pad[7:].view(n, H, W, 3)
+    assert torch.equal(fused.extract_u8(shifted, boxes, flip_w=flip), a)
+    fused.set_waves(((0, 4), (7, 0)))
+    assert torch.equal(fused.extract_u8(raw, boxes, flip_w=flip), a)
+    fused.close()
+    plain.close()
 
 
 @pytest.mark.parametrize("n", [100, 200, 256])
