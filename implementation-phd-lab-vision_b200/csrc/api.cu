@@ -12,6 +12,7 @@
 #include "../../include/phdfx.h"
 #include "conv_igemm_sm100.cuh"
 #include "conv_igemm_cg2_sm100.cuh"
+#include "conv_igemm_cg2_multi_sm100.cuh"
 #include "bottleneck_chain_sm100.cuh"
 #include "elementwise_sm100.cuh"
 #include "stem_pool_sm100.cuh"
@@ -93,6 +94,7 @@ struct phdfx {
   bool use_rev = true;              // PHDFX_NO_REV=1: every launch walks its tiles in ascending order
   bool use_halo = true;             // PHDFX_NO_HALO=1: 3x3/1 convs of layer1 / layer2 through the im2col path
   bool use_small_n = true;          // PHDFX_NO_SMALL_N=1: keep 256-wide N tiles for launches with few tiles
+  bool use_multi = true;            // PHDFX_NO_MULTI=1: consecutive CTA-pair convs of a block as separate launches
   int fuse_k1 = 1;                  // K1 inside the stem kernel: 1 = where it pays (stem_can_fuse_k1), 0 = never
                                     // (PHDFX_NO_FUSE_K1=1), 2 = whenever the rows fit (PHDFX_FUSE_K1=1; tests)
   bool use_flags = false;           // PHDFX_FLAGS=1: launches follow their predecessor's frame progress counters
@@ -450,10 +452,9 @@ struct LaunchDep {
   uint32_t* sig = nullptr;
 };
 
-int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, const void* res, void* out, int n,
-                cudaStream_t st, int rev = 0, long long* trace = nullptr, const LaunchDep& dep = LaunchDep()) {
+ConvParams conv_params(const phdfx_t* h, const phdfx_layer_desc& L, const Geo& g, const void* res, void* out, int n,
+                       int rev, long long* trace, const LaunchDep& dep) {
   const bool has_res = res != nullptr;
-  const Geo g = geometry(h, L, n);
   ConvParams p{};
   p.Cout = L.cout;
   p.num_kb = g.num_kb;
@@ -489,7 +490,13 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, co
     p.m_tiles = (n + 1) / 2;
   else
     p.m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  return p;
+}
 
+int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, const void* res, void* out, int n,
+                cudaStream_t st, int rev = 0, long long* trace = nullptr, const LaunchDep& dep = LaunchDep()) {
+  const Geo g = geometry(h, L, n);
+  const ConvParams p = conv_params(h, L, g, res, out, n, rev, trace, dep);
   if (g.cg2) {
     if (g.mode == MODE_TILED) return launch_conv_cg2_t<MODE_TILED>(h, maps, p, st);
     return launch_conv_cg2_t<MODE_IM2COL>(h, maps, p, st);
@@ -513,6 +520,80 @@ int launch_conv(phdfx_t* h, const phdfx_layer_desc& L, const LayerMaps& maps, co
   }
 }
 
+
+// ---- up to three consecutive CTA-pair convs in one launch (conv_igemm_cg2_multi_sm100.cuh) ---------------------------
+// layers [i, i + count): maps[k] their tensor maps, outs[k] their output pointers; phase k publishes its progress in the
+// counter row of layer i + k, which the pass's first launch (the fused stem) has zeroed.
+int launch_conv_multi(phdfx_t* h, int i, int count, const LayerMaps* const* maps, void* const* outs, int n,
+                      cudaStream_t st, int rev) {
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(conv_igemm_cg2_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cg2Cfg::SMEM_BYTES));
+    attr_set[h->device & 63] = true;
+  }
+  Cg2MultiMaps mm;
+  Cg2MultiParams mp{};
+  mp.n_phases = count;
+  int total = 0;
+  for (int k = 0; k < count; ++k) {
+    const auto& L = h->layers[i + k];
+    const Geo g = geometry(h, L, n);
+    LaunchDep dep;
+    const size_t row = static_cast<size_t>(h->max_frames) + 1;
+    if (k > 0) {
+      const auto& A = h->layers[i + k - 1];
+      const Geo ga = geometry(h, A, n);
+      dep.wait = h->d_ctrs + static_cast<size_t>(i + k - 1) * row;
+      dep.full = static_cast<uint32_t>(ga.P * ga.Q) * static_cast<uint32_t>(A.cout / 64);
+    }
+    if (k + 1 < count) dep.sig = h->d_ctrs + static_cast<size_t>(i + k) * row;
+    mp.ph[k] = conv_params(h, L, g, nullptr, outs[k], n, rev, nullptr, dep);
+    mp.mode[k] = g.mode;
+    mp.begin[k] = total;
+    total += ((mp.ph[k].m_tiles + 1) / 2) * mp.ph[k].n_tiles;
+    mm.a[k] = maps[k]->a;
+    mm.b[k] = maps[k]->b;
+    mm.o[k] = maps[k]->o;
+    mm.a2[k] = maps[k]->a2;
+  }
+  for (int k = count; k < kMaxPhases; ++k) mm.a[k] = mm.b[k] = mm.o[k] = mm.a2[k] = mm.a[0];
+  for (int k = count; k <= kMaxPhases; ++k) mp.begin[k] = total;
+  const int max_pairs = h->num_sms / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  for (int k = 1; k < count; ++k) mp.ph[k].wait_ctas = static_cast<uint32_t>(2 * pairs);
+  CUDA_TRY(h, launch_pdl(conv_igemm_cg2_multi_kernel, dim3(2 * pairs), dim3(kNumThreads), Cg2Cfg::SMEM_BYTES, st, mm,
+                         mp));
+  h->last_launches++;
+  return 0;
+}
+
+// how many layers starting at i can run as one multi-phase CTA-pair launch on n frames (1 = no grouping)
+int multi_span_at(const phdfx_t* h, int i, int n) {
+  const int nl = static_cast<int>(h->layers.size());
+  auto eligible = [&](int j) {
+    if (j >= nl || h->chain_span[j] != 0) return false;
+    const auto& L = h->layers[j];
+    return L.kind == PHDFX_CONV && !L.gap && L.res_buf < 0 && geometry(h, L, n).cg2;
+  };
+  if (!eligible(i)) return 1;
+  int count = 1;
+  while (count < kMaxPhases && eligible(i + count)) {
+    const auto& B = h->layers[i + count];
+    const auto& A = h->layers[i + count - 1];
+    if (B.in_buf != A.out_buf) break;
+    bool ok = true;
+    for (int k = 0; k < count; ++k) {
+      const auto& E = h->layers[i + k];
+      // B reads nothing else the group writes, and writes nothing the group reads or writes
+      if (B.in2_buf == E.out_buf) ok = false;
+      if (B.out_buf == E.in_buf || B.out_buf == E.in2_buf || B.out_buf == E.out_buf) ok = false;
+    }
+    if (!ok) break;
+    ++count;
+  }
+  return count;
+}
 
 // ---- bottleneck chain (bottleneck_chain_sm100.cuh): layer1 (56x56, width 64) and layer2 (28x28, width 128) ---------
 bool is_chain_conv2(const phdfx_layer_desc& L) {
@@ -795,9 +876,14 @@ int k1_launch(phdfx_t* h, const uint8_t* d_frames, int n, int H, int W, const in
 // Resolves where the launch's tensors live under the stage's addressing rules (absolute frame number, or the stage's
 // wave-local region), fetches / builds the tensor maps for exactly those pointers and that frame count, and launches
 // (dry = build the maps only).  *span = execution-list entries covered (a fused chain covers 2 or 3).
+struct ResolvedConv {  // run_launch(..., &resolved): the launch's tensor maps and output pointer instead of launching it
+  const LayerMaps* maps = nullptr;
+  void* out = nullptr;
+};
+
 int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, const void* ext_in, bool buf0_local,
                float* d_feats, cudaStream_t st, int rev, bool dry, int* span, const LaunchDep& dep = LaunchDep(),
-               bool zero_ctrs = false, const Source* u8 = nullptr) {
+               bool zero_ctrs = false, const Source* u8 = nullptr, ResolvedConv* resolved = nullptr) {
   const auto& L = h->layers[i];
   // frame f of a tensor lives at base + f * (the TENSOR's bytes per frame) — the dense layout an un-waved pass uses, so
   // a stage may read what a differently-waved stage wrote; wave-local tensors sit at frame 0 (+ slot) of their buffer
@@ -873,6 +959,11 @@ int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, cons
     }
     cache.push_back(e);
     maps = &cache.back().maps;
+  }
+  if (resolved != nullptr) {
+    resolved->maps = maps;
+    resolved->out = const_cast<void*>(k.out);
+    return 0;
   }
   if (dry) return 0;
   if (L.kind == PHDFX_STEM_POOL) return launch_stem_pool(h, L, maps->o, at(L.in_buf, in_bpf(L)), m, st, zero_ctrs, u8);
@@ -957,6 +1048,7 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   if (const char* e = getenv("PHDFX_NO_CG2")) h->use_cg2 = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_REV")) h->use_rev = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_NO_SMALL_N")) h->use_small_n = !(e[0] == '1');
+  if (const char* e = getenv("PHDFX_NO_MULTI")) h->use_multi = !(e[0] == '1');
   if (const char* e = getenv("PHDFX_FUSE_K1")) h->fuse_k1 = e[0] == '1' ? 2 : 1;
   if (const char* e = getenv("PHDFX_NO_FUSE_K1")) h->fuse_k1 = e[0] == '1' ? 0 : h->fuse_k1;
   if (const char* e = getenv("PHDFX_FLAGS")) h->use_flags = e[0] == '1';
@@ -1146,6 +1238,16 @@ static int forward_impl(phdfx_t* h, const Source& src, int n, float* d_feats, cu
   const std::vector<char> link = plan_links(h, n);
   bool any_link = false;
   for (char c : link) any_link |= c != 0;
+  // consecutive CTA-pair convs of a block as ONE multi-phase launch (conv_igemm_cg2_multi_sm100.cuh); the phases meet on
+  // frame progress counters, which the fused stem zeroes at the start of the pass
+  const bool multi_ok = h->use_multi && !h->use_flags && timed == nullptr && h->d_ctrs && !h->d_cta_ts && S == 1 &&
+                        h->stages[0].wave == 0 && h->layers[0].kind == PHDFX_STEM_POOL;
+  if (multi_ok)
+    for (int i = 0; i < static_cast<int>(h->layers.size()) && !any_link;) {
+      const int ms = multi_span_at(h, i, n);
+      any_link = ms > 1;
+      i += h->chain_span[i] > 0 ? h->chain_span[i] : ms;
+    }
   int prev_rev = 1;
   std::vector<int> done(S, 0), idx(S, 0);
   const bool buf0_local = (h->sched_flags & PHDFX_SCHED_REUSE) && src.frames != nullptr && h->stages[0].wave > 0;
@@ -1181,6 +1283,23 @@ static int forward_impl(phdfx_t* h, const Source& src, int n, float* d_feats, cu
       prev_rev = rev;
       int span = 1;
       mark(i);
+      const int mspan = multi_ok ? multi_span_at(h, i, m) : 1;
+      if (mspan > 1) {
+        ResolvedConv rc[kMaxPhases];
+        const LayerMaps* gm[kMaxPhases];
+        void* go[kMaxPhases];
+        for (int k = 0; k < mspan; ++k) {
+          int sp1 = 1;
+          if (int e = run_launch(h, sg, i + k, f0, m, 0, src.d_in, buf0_local, d_feats, st, rev, false, &sp1, LaunchDep(),
+                                 false, nullptr, &rc[k]))
+            return e;
+          gm[k] = rc[k].maps;
+          go[k] = rc[k].out;
+        }
+        if (int e = launch_conv_multi(h, i, mspan, gm, go, m, st, rev)) return e;
+        i += mspan;
+        continue;
+      }
       LaunchDep dep;
       if (link[i]) {
         int a = i - 1;  // the launch in front (links only exist between single-entry launches)

@@ -294,7 +294,7 @@ def test_chains_are_bit_identical_to_per_conv_kernels(backbone):
         del os.environ["PHDFX_NO_CHAIN"]
     a = fused.extract_u8(frames, None)
     b = plain.extract_u8(frames, None)
-    assert fused.launches == 40 and plain.launches == 49
+    assert plain.launches - fused.launches == 9  # 6 chains replace 15 launches (both group layer3's CTA-pair convs alike)
     assert torch.equal(a, b)
     fused.close()
     plain.close()
@@ -493,9 +493,10 @@ def test_full_batch_256_properties():
     waved_launches = e.launches
     e.set_waves(((0, 0),))
     whole = e.extract_u8(frames, None)
-    # un-waved: fused K1/stem/maxpool + 39 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 ->
-    # next conv1 chains and layer2's conv2 -> conv3 chains are one launch each), all ours
-    assert e.launches == 40 and waved_launches >= 40
+    # un-waved: fused K1/stem/maxpool + 28 conv launches (4 down-samples ride in conv3; layer1's conv2 -> conv3 ->
+    # next conv1 chains and layer2's conv2 -> conv3 chains are one launch each; in layer3 / layer4 every block's conv1 ->
+    # conv2 [-> conv3 + down-sample] is one multi-phase CTA-pair launch), all ours
+    assert e.launches == 29 and waved_launches >= 29
     assert torch.equal(big, whole)
     small = torch.cat([e.extract_u8(frames[i:i + 37].contiguous(), None) for i in range(0, 256, 37)])
     assert torch.equal(big, small)
@@ -609,6 +610,36 @@ def test_k1_inside_the_stem_equals_k1_as_a_launch(backbone, H, W, box, flip, n):
     fused.set_waves(((0, 4), (7, 0)))
     assert torch.equal(fused.extract_u8(raw, boxes, flip_w=flip), a)
     fused.close()
+    plain.close()
+
+
+@pytest.mark.parametrize("n", [64, 100, 200, 256])
+def test_multi_phase_launches_are_bit_identical(backbone, n):
+    """conv1 -> conv2 [-> conv3 + down-sample] of a layer3 / layer4 block run as ONE multi-phase CTA-pair launch
+    (csrc/conv_igemm_cg2_multi_sm100.cuh): every tile is computed as by the per-conv kernel, the phases meet on per-frame
+    progress counters.  Features equal those of a handle created with PHDFX_NO_MULTI=1 bit for bit — repeated plain
+    launches (a missed dependency would be a race) and graph replay."""
+    multi = phdfx.B200Backbone(backbone, device=0, max_frames=n)
+    os.environ["PHDFX_NO_MULTI"] = "1"
+    try:
+        plain = phdfx.B200Backbone(backbone, device=0, max_frames=n)
+    finally:
+        del os.environ["PHDFX_NO_MULTI"]
+    frames = torch.from_numpy(R.seeded_frames(n, 224, 224, 500 + n)).cuda()
+    want = plain.extract_u8(frames, None).clone()
+    assert plain.launches == 40
+    out = torch.empty(n, 2048, device="cuda")
+    for _ in range(6):
+        out.fill_(float("nan"))
+        multi.extract_u8(frames, None, out=out)
+        assert torch.equal(out, want), n
+    assert multi.launches == (29 if n >= 100 else 33), multi.launches  # at n = 64 layer4's convs use narrow 1-CTA tiles
+    g = multi.capture_extract(frames, None)
+    for _ in range(6):
+        assert torch.equal(g.replay(), want), n
+    # per-launch timing keeps one launch per conv (and the same bits)
+    assert len(multi.forward_timed(multi.preprocess_u8(frames, None))[1]) == 40
+    multi.close()
     plain.close()
 
 

@@ -1,6 +1,7 @@
 """Small, deterministic launch sequences for ncu.
 
-    python tools/ncu_target.py step [batch]          # 2 warm-up steps + 1 step of the whole hot path (41 launches each: K1 + 40 trunk launches)
+    python tools/ncu_target.py step [batch]          # 3 steps of the whole hot path from uint8 frames (40 launches each: K1 rides in the stem kernel)
+    python tools/ncu_target.py trunk [batch]         # K1, then 3 passes of the trunk on its NHWC4p output (40 launches each) — what bench.py's roofline leg times
     python tools/ncu_target.py layers 0,3,5 [batch]  # each listed layer of the execution list twice via phdfx_run_layer
 """
 import sys
@@ -17,7 +18,16 @@ from phdfx import synthetic as R  # noqa: E402
 
 def main():
     mode = sys.argv[1]
-    if mode == "step":
+    if mode == "trunk":
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+        eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
+        frames = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device="cuda")
+        x4 = eng.preprocess_u8(frames, None)
+        for _ in range(3):
+            eng.forward_nhwc4p(x4)
+        torch.cuda.synchronize()
+        print("trunk done, launches per pass:", eng.last_launch_count)
+    elif mode == "step":
         n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
         eng = phdfx.B200Backbone(R.seeded_backbone(), device=0, max_frames=n)
         if len(sys.argv) > 3:  # frame-wave schedule, e.g. 0:32,7:0 [reuse 0|1]
