@@ -132,8 +132,9 @@ bottleneck_chain_kernel(const __grid_constant__ CUtensorMap mapH,   // t1 [n][W]
   uint64_t* acc3_empty = acc3_full + 1;                     // [1] epilogue -> MMA (NH == 2): the low half is drained
   uint64_t* acc1_full = acc3_empty + 1;
   uint64_t* t2_full = acc1_full + 1;                        // [1] epilogue (8 warps) -> MMA: bf16 t2 is in TMEM
-  uint64_t* out_full = t2_full + 1;                         // [1] epilogue -> MMA: bf16 block output is in TMEM
-  uint64_t* res_full = out_full + 1;                        // [NB] loader -> epilogue: buffer free / residual landed
+  uint64_t* out_full = t2_full + 1;                         // [4] epilogue -> MMA: 64-channel group g of the bf16 block
+                                                            // output is in TMEM (K block g of the next conv1)
+  uint64_t* res_full = out_full + 4;                        // [NB] loader -> epilogue: buffer free / residual landed
   uint64_t* st_ready = res_full + NB;                       // [NB] epilogue -> DMA: group staged
   uint64_t* st_free = st_ready + NB;                        // [NB] DMA -> loader: the store has left shared memory
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(st_free + NB);
@@ -191,7 +192,7 @@ bottleneck_chain_kernel(const __grid_constant__ CUtensorMap mapH,   // t1 [n][W]
     mbar_init(acc3_empty, kEpiWarps);
     mbar_init(acc1_full, 1);
     mbar_init(t2_full, kEpiWarps);
-    mbar_init(out_full, kEpiWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&out_full[i], kEpiWarps);
     for (int i = 0; i < NB; ++i) {
       mbar_init(&res_full[i], 1);
       mbar_init(&st_ready[i], kEpiWarps);
@@ -388,11 +389,13 @@ bottleneck_chain_kernel(const __grid_constant__ CUtensorMap mapH,   // t1 [n][W]
       }
       if (N1 > 0) {
         // conv1n(k): A = bf16 block output parked over the conv3 accumulator columns (K block kb, K step s at column
-        // 64*kb + 32*(s/2) + 8*(s%2)), B streams through the ring as [64 rows][64 K] tiles
-        mbar_wait(out_full, k & 1);
-        mark(k, 3);
-        tc_fence_after();
+        // 64*kb + 32*(s/2) + 8*(s%2)), B streams through the ring as [64 rows][64 K] tiles.  Each K block is issued as
+        // soon as the epilogue warps have parked ITS 64 channels, so the conv runs under the residual epilogue of the
+        // groups behind it instead of after the whole of it (the epilogue warps used to idle ~1 300 cycles per tile here)
         for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&out_full[kb], k & 1);
+          if (kb == 0) mark(k, 3);
+          tc_fence_after();
           for (int nh = 0; nh < N1 / 64; ++nh) {
             mbar_wait(&ring_full[stage], phase);
             tc_fence_after();
@@ -525,13 +528,13 @@ bottleneck_chain_kernel(const __grid_constant__ CUtensorMap mapH,   // t1 [n][W]
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&st_ready[b]);
+        if (N1 > 0) {  // K block gg of the next conv1 may go
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_full[gg]);
+        }
         if (warp == 4 && h == 0) mark(k, 8 + gg);
-      }
-      if (N1 > 0) {
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(out_full);
       }
       if (NH == 2 && h == 0) {  // the MMA warp may overwrite the accumulator with the high half
         tc_fence_before();

@@ -206,7 +206,7 @@ class B200Backbone:
 
     def capture_extract(self, frames: torch.Tensor, boxes: Optional[torch.Tensor] = None, flip_w: bool = False,
                         out: Optional[torch.Tensor] = None) -> "ExtractGraph":
-        """Capture extract_u8 on exactly these tensors into a CUDA graph (41 launches -> one graph launch)."""
+        """Capture extract_u8 on exactly these tensors into a CUDA graph (its 29-42 launches -> one graph launch)."""
         return ExtractGraph(self, frames, boxes, flip_w, out)
 
     def _check_jitter(self, jitter: torch.Tensor, n: int):
@@ -392,6 +392,7 @@ class CapturedCall:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.result = fn()
+        self.launches = eng.last_launch_count  # kernels of the last engine call inside fn()
 
     def replay(self):
         self.graph.replay()
