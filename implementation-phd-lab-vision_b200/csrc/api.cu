@@ -766,12 +766,14 @@ int launch_stem_pool(phdfx_t* h, const phdfx_layer_desc& L, const CUtensorMap& m
     p.W = u8->W;
     p.boxes = u8->boxes;
     p.flip_w = u8->flip_w;
+#ifdef PHDFX_EXPERIMENTAL
     static long long* d_stem_trace = nullptr;
     if (getenv("PHDFX_STEM_TRACE")) {  // debug: phase clocks of one converter warp, printed after the launch (synchronises)
       if (!d_stem_trace) cudaMalloc(&d_stem_trace, 8 * sizeof(long long));
       cudaMemset(d_stem_trace, 0, 8 * sizeof(long long));
       p.trace = d_stem_trace;
     }
+#endif
     CUDA_TRY(h, launch_pdl(stem_pool_kernel<true>, dim3(grid), dim3(kSpFuseThreads), smem, st, map_out, p));
     if (p.trace) {
       long long t[8];
@@ -984,6 +986,9 @@ int run_launch(phdfx_t* h, const Stage& sg, int i, int f0, int m, int slot, cons
 std::vector<char> plan_links(const phdfx_t* h, int n) {
   const int nl = static_cast<int>(h->layers.size());
   std::vector<char> link(nl, 0);
+#ifndef PHDFX_EXPERIMENTAL
+  return link;  // the single-launch kernels carry the counter code only in experimental builds (conv_igemm_sm100.cuh)
+#endif
   if (!h->use_flags || !h->d_ctrs || h->num_sms != h->real_sms || h->stages.size() != 1 || h->stages[0].wave != 0 ||
       h->layers[0].kind != PHDFX_STEM_POOL)
     return link;
@@ -1054,7 +1059,9 @@ int phdfx_create(phdfx_t** out, int device_ordinal, int max_frames) {
   if (const char* e = getenv("PHDFX_FLAGS")) h->use_flags = e[0] == '1';
   if (const char* e = getenv("PHDFX_FLAG_MAX_MB")) h->flag_max_bytes = static_cast<size_t>(atoi(e)) << 20;
   h->real_sms = prop.multiProcessorCount;
+#ifdef PHDFX_EXPERIMENTAL
   if (const char* e = getenv("PHDFX_CTA_TRACE")) h->cta_trace_path = e;
+#endif
   if (const char* e = getenv("PHDFX_SM_CAP")) {  // experiments: run every persistent grid on fewer SMs
     const int cap = atoi(e);
     if (cap >= 2 && cap < h->num_sms) h->num_sms = cap & ~1;

@@ -436,7 +436,7 @@ bottleneck_chain_kernel(const __grid_constant__ CUtensorMap mapH,   // t1 [n][W]
           }
         }
       }
-      tma_store_wait_read<0>();  // the CTA may exit once its stores have left shared memory (conv_igemm_sm100.cuh)
+      tma_store_wait_all<0>();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (warps 4..11)

@@ -272,7 +272,7 @@ conv_igemm_cg2_multi_kernel(const __grid_constant__ Cg2MultiMaps maps, const __g
           }
         }
       }
-      tma_store_wait_read<0>();
+      tma_store_wait_all<0>();
       publish_phases(mp.n_phases);
     }
   } else if (warp == 3) {

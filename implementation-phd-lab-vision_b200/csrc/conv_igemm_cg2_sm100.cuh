@@ -160,7 +160,7 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
-  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 4] = global_timer_ns();  // kernel entry
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0) P_CTA_TS(p)[blockIdx.x * 6 + 4] = global_timer_ns();  // kernel entry
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
@@ -198,9 +198,9 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   griddep_launch_dependents();
-  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 0] = global_timer_ns();
-  if (p.wait_ctr == nullptr) griddep_wait();
-  if (p.cta_ts != nullptr && threadIdx.x == 0 && p.wait_ctr == nullptr) p.cta_ts[blockIdx.x * 6 + 1] = global_timer_ns();
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0) P_CTA_TS(p)[blockIdx.x * 6 + 0] = global_timer_ns();
+  if (P_WAIT(p) == nullptr) griddep_wait();
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0 && P_WAIT(p) == nullptr) P_CTA_TS(p)[blockIdx.x * 6 + 1] = global_timer_ns();
   unsigned long long dep_ns = 0;
 
   if (warp == 0) {
@@ -235,18 +235,18 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           ch = p0 * 2;
         }
       }
-      if (p.wait_ctr != nullptr) {  // frame progress counters: conv_igemm_sm100.cuh
-        const unsigned long long tw = p.cta_ts != nullptr ? global_timer_ns() : 0ull;
-        if (!dep_all) dep_all = dep_grid_done(p.wait_ctr + p.ctr_frames, p.wait_ctas);
+      if (P_WAIT(p) != nullptr) {  // frame progress counters: conv_igemm_sm100.cuh
+        const unsigned long long tw = P_CTA_TS(p) != nullptr ? global_timer_ns() : 0ull;
+        if (!dep_all) dep_all = dep_grid_done(P_WAIT(p) + p.ctr_frames, p.wait_ctas);
         if (!dep_all) {
           int f_lo, f_hi;
           frames_of(m_blk, &f_lo, &f_hi);
-          dep_wait_frames(p.wait_ctr, p.wait_full, f_lo, f_hi);
+          dep_wait_frames(P_WAIT(p), p.wait_full, f_lo, f_hi);
         }
-        if (p.cta_ts != nullptr) {
+        if (P_CTA_TS(p) != nullptr) {
           const unsigned long long now = global_timer_ns();
           dep_ns += now - tw;
-          if (lp == pair && lane == 0) p.cta_ts[blockIdx.x * 6 + 1] = now;
+          if (lp == pair && lane == 0) P_CTA_TS(p)[blockIdx.x * 6 + 1] = now;
         }
       }
       for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -326,7 +326,7 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const int m_blk = 2 * (pt / p.n_tiles) + static_cast<int>(rank);
         if (m_blk * kBlockM >= p.M) return;
         const int r1 = (m_blk + 1) * kBlockM < p.M ? (m_blk + 1) * kBlockM : p.M;
-        dep_signal_rows(p.sig_ctr, m_blk * kBlockM, r1, p.P * p.Q, GROUPS);
+        dep_signal_rows(P_SIG(p), m_blk * kBlockM, r1, p.P * p.Q, GROUPS);
       };
       for (int t = 0; t < J + LOOK; ++t) {
         if (t < J) {
@@ -345,18 +345,15 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const int m_blk = 2 * m_pair + static_cast<int>(rank);
           tma_store_2d(&mapO, stage_out + b * kStageOutBytes, n_blk * BN + g * kGroupCols, m_blk * kBlockM);
           tma_store_commit();
-          if (p.sig_ctr != nullptr && g == GROUPS - 1) {
+          if (P_SIG(p) != nullptr && g == GROUPS - 1) {
             // the pair's next accumulator is many K blocks away: wait until the tile has been WRITTEN and publish it
             tma_store_wait_all<0>();
             signal_tile(lp);
           }
         }
       }
-      if (p.sig_ctr != nullptr)
-        tma_store_wait_all<0>();
-      else
-        tma_store_wait_read<0>();  // see conv_igemm_sm100.cuh: the writes complete with the grid
-      if (p.sig_ctr != nullptr) red_release_gpu_add(p.sig_ctr + p.ctr_frames, 1u);  // this CTA has published everything
+      tma_store_wait_all<0>();
+      if (P_SIG(p) != nullptr) red_release_gpu_add(P_SIG(p) + p.ctr_frames, 1u);  // this CTA has published everything
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (warps 4..11, both CTAs)
@@ -424,10 +421,10 @@ conv_igemm_cg2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
   }
 
-  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 3] = dep_ns;
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0) P_CTA_TS(p)[blockIdx.x * 6 + 3] = dep_ns;
   tc_fence_before();
   __syncthreads();
-  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 2] = global_timer_ns();
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0) P_CTA_TS(p)[blockIdx.x * 6 + 2] = global_timer_ns();
   cluster_sync_all();  // neither CTA may exit (or free TMEM) while the other can still signal it
   if (warp == 2) {
     tc_fence_after();

@@ -73,6 +73,22 @@ struct ConvParams {
   long long* trace;   // debug (PHDFX_CONV_TRACE): CTA 0 writes clock64() of pipeline events, [tile < 32][32 events]
 };
 
+// Experimental code paths of the single-launch kernels are compiled in only with -DPHDFX_EXPERIMENTAL (PHDFX_EXPERIMENTAL=1
+// at build()): the per-CTA timeline (PHDFX_CTA_TRACE) and the frame progress counters BETWEEN launches (PHDFX_FLAGS=1).
+// Both are dead branches in a normal pass, yet they cost: batch-1 latency under graph replay 325.8 us with both, 320.4
+// without the timeline code, 320.6 without the counter code, 316.4 without either (40 launches of one tile each, where
+// every instruction in front of the first TMA load is on the critical path).  The multi-phase CTA-pair kernel uses the
+// counters in every build.
+#ifdef PHDFX_EXPERIMENTAL
+#define P_CTA_TS(p) ((p).cta_ts)
+#define P_WAIT(p) ((p).wait_ctr)
+#define P_SIG(p) ((p).sig_ctr)
+#else
+#define P_CTA_TS(p) (static_cast<unsigned long long*>(nullptr))
+#define P_WAIT(p) (static_cast<const uint32_t*>(nullptr))
+#define P_SIG(p) (static_cast<uint32_t*>(nullptr))
+#endif
+
 constexpr int kBlockM = 128;
 constexpr int kNumThreads = 384;
 constexpr int kEpiThreads = 256;   // warps 4..11
@@ -207,7 +223,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
-  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 4] = global_timer_ns();  // kernel entry
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0) P_CTA_TS(p)[blockIdx.x * 6 + 4] = global_timer_ns();  // kernel entry
   const int num_tiles = p.m_tiles * p.n_tiles;
   // debug timeline: event e of this CTA's k-th tile (CTA 0 only, first 32 tiles)
   auto mark = [&](int k, int e) {
@@ -253,9 +269,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's
   // tail; nothing below touches activations before the previous grid has completed.
   griddep_launch_dependents();
-  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 0] = global_timer_ns();
-  if (p.wait_ctr == nullptr) griddep_wait();
-  if (p.cta_ts != nullptr && threadIdx.x == 0 && p.wait_ctr == nullptr) p.cta_ts[blockIdx.x * 6 + 1] = global_timer_ns();
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0) P_CTA_TS(p)[blockIdx.x * 6 + 0] = global_timer_ns();
+  if (P_WAIT(p) == nullptr) griddep_wait();
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0 && P_WAIT(p) == nullptr) P_CTA_TS(p)[blockIdx.x * 6 + 1] = global_timer_ns();
   unsigned long long dep_ns = 0;
 
   if (warp == 0) {
@@ -314,20 +330,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           cn = m_blk / tpf;
           ch = (m_blk - cn * tpf) * p.halo_rt - 1;  // first input row of the patch (-1 = zero halo)
         }
-        if (p.wait_ctr != nullptr) {
+        if (P_WAIT(p) != nullptr) {
           // frames this tile reads from the previous launch (= the frames of its output rows); then read ahead for
           // the next tile of this CTA
           int f_lo, f_hi;
-          const unsigned long long tw = p.cta_ts != nullptr ? global_timer_ns() : 0ull;
-          if (!dep_all) dep_all = dep_grid_done(p.wait_ctr + p.ctr_frames, p.wait_ctas);
+          const unsigned long long tw = P_CTA_TS(p) != nullptr ? global_timer_ns() : 0ull;
+          if (!dep_all) dep_all = dep_grid_done(P_WAIT(p) + p.ctr_frames, p.wait_ctas);
           if (!dep_all) {
             frames_of(m_blk, &f_lo, &f_hi);
-            dep_wait_frames(p.wait_ctr, p.wait_full, f_lo, f_hi);
+            dep_wait_frames(P_WAIT(p), p.wait_full, f_lo, f_hi);
           }
-          if (p.cta_ts != nullptr) {
+          if (P_CTA_TS(p) != nullptr) {
             const unsigned long long now = global_timer_ns();
             dep_ns += now - tw;
-            if (lt == static_cast<int>(blockIdx.x) && lane == 0) p.cta_ts[blockIdx.x * 6 + 1] = now;
+            if (lt == static_cast<int>(blockIdx.x) && lane == 0) P_CTA_TS(p)[blockIdx.x * 6 + 1] = now;
           }
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -484,7 +500,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int tile = p.rev ? num_tiles - 1 - lt : lt;
         const int m_blk = tile / p.n_tiles;
         const int r1 = (m_blk + 1) * kBlockM < p.M ? (m_blk + 1) * kBlockM : p.M;
-        dep_signal_rows(p.sig_ctr, m_blk * kBlockM, r1, p.P * p.Q, GROUPS);
+        dep_signal_rows(P_SIG(p), m_blk * kBlockM, r1, p.P * p.Q, GROUPS);
       };
       for (int t = 0; t < J + LOOK; ++t) {
         if (t < J) {
@@ -532,7 +548,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
             tma_store_commit();
             if (g < 4) mark(u / GROUPS, 12 + g);
-            if ((MODE == MODE_TILED || MODE == MODE_IM2COL) && p.sig_ctr != nullptr) {
+            if ((MODE == MODE_TILED || MODE == MODE_IM2COL) && P_SIG(p) != nullptr) {
               // Publish a tile once its stores have been WRITTEN (wait_group without .read).  MMA-bound launches (long K)
               // emit a tile's groups in a burst and then nothing for a long time: wait right away, this thread has nothing
               // else to do.  Epilogue-bound launches emit groups continuously: publish kSigLag groups late, when the wait
@@ -550,19 +566,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           }
         }
       }
-      // a CTA may exit once its stores have been READ out of shared memory: the writes complete with the grid, which is
-      // what the next launch waits for; only a launch that publishes progress itself has to see them written first
-      if (MODE != MODE_GAP) {
-        if (p.sig_ctr != nullptr)
-          tma_store_wait_all<0>();
-        else
-          tma_store_wait_read<0>();
-      }
-      if ((MODE == MODE_TILED || MODE == MODE_IM2COL) && p.sig_ctr != nullptr) {
+      // (exiting on wait_group.read — the writes then complete with the grid — was measured: no change at batch 256,
+      // and +0.3 us per launch at batch 1, where the next launch's griddepcontrol.wait sits right behind this exit)
+      if (MODE != MODE_GAP) tma_store_wait_all<0>();
+      if ((MODE == MODE_TILED || MODE == MODE_IM2COL) && P_SIG(p) != nullptr) {
         if (!sig_now)
           for (int w = (J > kSigLag ? J - kSigLag : 0); w < J; ++w)
             if (w % GROUPS == GROUPS - 1) signal_tile(w / GROUPS);
-        red_release_gpu_add(p.sig_ctr + p.ctr_frames, 1u);  // this CTA has published everything
+        red_release_gpu_add(P_SIG(p) + p.ctr_frames, 1u);  // this CTA has published everything
       }
     }
   } else if (warp >= 4) {
@@ -698,10 +709,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   }
 
-  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 3] = dep_ns;
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0) P_CTA_TS(p)[blockIdx.x * 6 + 3] = dep_ns;
   tc_fence_before();
   __syncthreads();
-  if (p.cta_ts != nullptr && threadIdx.x == 0) p.cta_ts[blockIdx.x * 6 + 2] = global_timer_ns();
+  if (P_CTA_TS(p) != nullptr && threadIdx.x == 0) P_CTA_TS(p)[blockIdx.x * 6 + 2] = global_timer_ns();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

@@ -316,7 +316,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
           }
         }
       }
-      tma_store_wait_read<0>();  // the CTA may exit once its stores have left shared memory (conv_igemm_sm100.cuh)
+      tma_store_wait_all<0>();
     }
   }
   } else if (FUSE_K1 && warp >= 12) {
@@ -391,7 +391,11 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap mapO, const StemPoolParams 
       return g;
     };
     long long tr[6] = {0, 0, 0, 0, 0, 0};
+#ifdef PHDFX_EXPERIMENTAL
     const bool tracing = p.trace != nullptr && blockIdx.x == 0 && cw == 0;
+#else
+    constexpr bool tracing = false;
+#endif
     auto tick = [&](int k, long long& t) {
       if (tracing) {
         const long long now = clock64();

@@ -167,7 +167,8 @@ int phdfx_run_chain(phdfx_t* h, int first_layer_id, const void* d_t1, const void
 int phdfx_set_schedule(phdfx_t* h, const int32_t* first_layer, const int32_t* wave_frames, int n_stages, int flags);
 int phdfx_get_schedule(const phdfx_t* h, int32_t* first_layer, int32_t* wave_frames, int cap, int* flags);
 
-/* Tile-granular dependencies between launches (opt-in: PHDFX_FLAGS=1 in the environment at phdfx_create).  A launch
+/* Tile-granular dependencies between launches (experimental: a library built with PHDFX_EXPERIMENTAL=1, and
+ * PHDFX_FLAGS=1 in the environment at phdfx_create).  A launch
  * starts (programmatic dependent launch) while its predecessor drains but touches no activation before that grid has
  * completed.  With the switch on, where it is safe — two consecutive plain conv launches on full grids, the second
  * reading only the first's output of at most PHDFX_FLAG_MAX_MB (default 64) MB — phdfx_forward instead lets the second

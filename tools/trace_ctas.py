@@ -1,6 +1,7 @@
 """CTA timeline of one pass at batch N (PHDFX_CTA_TRACE): for every conv launch of layer3 / layer4, when its CTAs became
 resident, when their first tile's inputs were available, when they exited — relative to the previous launch's last exit.
 
+    PHDFX_EXPERIMENTAL=1 python -c "import __graft_entry__ as g; g.build(force=True)"     (the timeline code is not in a normal build)
     python tools/trace_ctas.py [batch] > gpurun_out/cta_trace.txt        (PHDFX_FLAGS=1: with frame progress links)
 """
 import os
