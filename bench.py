@@ -572,6 +572,13 @@ def run_b200(args):
                                    f"layer1/layer2 conv2 -> conv3 [-> next conv1]) + conv_igemm[_cg2]_kernel; "
                                    f"{n_trunk} launches per step",
                          "trunk_ms_per_step": trunk_ms, "flop_per_frame": FLOP_PER_FRAME,
+                         # the same FLOP count over the WHOLE step of the `value` region (uint8 frames in, K1's work done
+                         # by the stem kernel's converter warps and not counted): the production path is faster than the
+                         # trunk-only leg above, whose stem reads a 106 MB NHWC4p tensor instead of 38.5 MB of uint8
+                         "whole_step": {"ms_per_step": ms_max / K,
+                                        "achieved": BATCH * FLOP_PER_FRAME / (ms_max / K / 1e3) / 1e12,
+                                        "frac": BATCH * FLOP_PER_FRAME / (ms_max / K / 1e3) / 1e12 / pk["bf16_burst"],
+                                        "note": "per rank; at N > 1 the region also holds the NCCL gather"},
                          "frac_of_sustained_peak": achieved_tf / pk["bf16_sustained"],
                          "peak_sustained": pk["bf16_sustained"], "peak_source": pk["source"],
                          "sustained": {"achieved": sus_tf, "peak": pk["bf16_sustained"],
